@@ -1,0 +1,142 @@
+"""Seeded input builders for the parity cases (numpy only).
+
+Shared by tests/golden/make_golden.py (which runs the LIVE reference on them in the
+build container and commits its outputs) and by the tests (which run the oracle and
+the CUDA path on the same inputs).  Every input is regenerated from its seed, so the
+fixtures hold reference OUTPUTS only.
+"""
+import math
+import numpy as np
+
+from neuralrgbd_b200 import synth, arch
+
+FX = FY = 585.0          # DSO/cam_info_7scenes.mat: 640x480, fx=fy=585, cx=320, cy=240
+CX, CY = 320.0, 240.0
+
+
+def cam_for(make_cam, w, h):
+    return make_cam(FX, FY, CX, CY, [w, h])
+
+
+def _feat_pair(rng, C, h, w, V, mix=0.7):
+    ref = synth.smooth_image(rng, C, h, w)
+    src = np.stack([mix * ref + (1 - mix) * synth.smooth_image(rng, C, h, w) for _ in range(V)])
+    return ref[None], src[None]
+
+
+def _poses(rng, V, step_t=0.03, step_rot=0.7):
+    """V relative poses E_src . E_ref^-1 around a reference in the middle of a track."""
+    exts = synth.camera_track(rng, V + 1, step_t, step_rot)
+    r = V // 2
+    inv_ref = np.linalg.inv(exts[r])
+    return np.stack([exts[i].dot(inv_ref) for i in range(V + 1) if i != r]).astype(np.float32)
+
+
+def sweep_case(name):
+    """-> dict(ref, src, d, R, t, w, h, sigma, feat_dist)."""
+    cfg = {
+        # BASELINE.json configs[0]: 320x256 ref + 1 source, 32 planes, C=67
+        'c1_320x256_v1_d32_c67': dict(seed=11, h=256, w=320, C=67, V=1, D=32, dist='L2'),
+        'c1_320x256_v1_d32_c3': dict(seed=12, h=256, w=320, C=3, V=1, D=32, dist='L2'),
+        'small_v4_d32_c67_L2': dict(seed=13, h=64, w=80, C=67, V=4, D=32, dist='L2'),
+        'small_v4_d32_c67_L1': dict(seed=13, h=64, w=80, C=67, V=4, D=32, dist='L1'),
+        'ragged_v3_d7_c5': dict(seed=14, h=37, w=53, C=5, V=3, D=7, dist='L2'),
+        # d_min = 0 plane (test_KVNet.py:58 default) and a camera moved *behind* the
+        # reference so that P_z <= 0 for near planes (the +1e-10 path, homography.py:438)
+        'dzero_behind_v2_d16_c8': dict(seed=15, h=48, w=64, C=8, V=2, D=16, dist='L2', d_min=0.0,
+                                        d_max=2.0, step_t=0.6),
+        'identity_v1_d8_c16': dict(seed=16, h=48, w=64, C=16, V=1, D=8, dist='L2', identity=True),
+    }[name]
+    rng = np.random.RandomState(cfg['seed'])
+    ref, src = _feat_pair(rng, cfg['C'], cfg['h'], cfg['w'], cfg['V'])
+    poses = _poses(rng, cfg['V'], cfg.get('step_t', 0.03))
+    if cfg.get('identity'):
+        poses = np.stack([np.eye(4, dtype=np.float32)] * cfg['V'])
+        src = np.repeat(ref[:, None], cfg['V'], axis=1)
+    if 'step_t' in cfg:       # push the source cameras along +z of the reference (points fall behind)
+        poses[:, 2, 3] += np.float32(0.5)
+    d = synth.d_candidates(cfg['D'], cfg.get('d_min', 0.1), cfg.get('d_max', 5.0))
+    return dict(ref=ref, src=src, d=d, R=np.ascontiguousarray(poses[:, :3, :3]),
+                t=np.ascontiguousarray(poses[:, :3, 3]), w=cfg['w'], h=cfg['h'], sigma=10.0,
+                feat_dist=cfg['dist'])
+
+
+SWEEP_CASES = ['c1_320x256_v1_d32_c67', 'c1_320x256_v1_d32_c3', 'small_v4_d32_c67_L2',
+               'small_v4_d32_c67_L1', 'ragged_v3_d7_c5', 'dzero_behind_v2_d16_c8', 'identity_v1_d8_c16']
+
+
+def warp_case(name):
+    cfg = {'warp_v4_d32': dict(seed=21, h=64, w=80, V=4, D=32),
+           'warp_v2_d5_ragged': dict(seed=22, h=33, w=47, V=2, D=5)}[name]
+    rng = np.random.RandomState(cfg['seed'])
+    imgs = [synth.smooth_image(rng, 3, cfg['h'], cfg['w'])[None] for _ in range(cfg['V'])]
+    poses = _poses(rng, cfg['V'])
+    d = synth.d_candidates(cfg['D'])
+    return dict(imgs=imgs, d=d, R=[np.ascontiguousarray(p[:3, :3]) for p in poses],
+                t=[np.ascontiguousarray(p[:3, 3]) for p in poses], w=cfg['w'], h=cfg['h'])
+
+
+WARP_CASES = ['warp_v4_d32', 'warp_v2_d5_ragged']
+
+
+def resample_case(name):
+    cfg = {'resample_pose_d32': dict(seed=31, h=64, w=80, D=32),
+           'resample_identity_d16': dict(seed=32, h=48, w=64, D=16, identity=True),
+           'resample_dnew_d16': dict(seed=33, h=48, w=64, D=16, d_new=True),
+           'resample_bigmove_d12': dict(seed=34, h=40, w=56, D=12, step_t=0.5)}[name]
+    rng = np.random.RandomState(cfg['seed'])
+    D, h, w = cfg['D'], cfg['h'], cfg['w']
+    logits = 3.0 * synth.smooth_image(rng, D, h, w)
+    m = logits.max(axis=0, keepdims=True)
+    vol = (logits - m - np.log(np.exp(logits - m).sum(axis=0, keepdims=True)))[None].astype(np.float32)
+    exts = synth.camera_track(rng, 2, cfg.get('step_t', 0.03))
+    rel = np.linalg.inv(exts[1].dot(np.linalg.inv(exts[0]))).astype(np.float32)
+    if cfg.get('identity'):
+        rel = np.eye(4, dtype=np.float32)
+    d = synth.d_candidates(D)
+    d_new = synth.d_candidates(D, 0.3, 4.0) if cfg.get('d_new') else None
+    return dict(vol=vol, rel=rel, d=d, d_new=d_new, w=w, h=h, pad=math.log(1.0 / D))
+
+
+RESAMPLE_CASES = ['resample_pose_d32', 'resample_identity_d16', 'resample_dnew_d16', 'resample_bigmove_d12']
+
+
+def kvnet_case(name):
+    """Full KVNET.forward / streaming cases. The CNN needs H/4, W/4 >= 64 (SPP
+    AvgPool2d(64), psm_submodule.py:103) so 256x256 is the smallest legal frame."""
+    cfg = {'kvnet_256_d16': dict(seed=41, H=256, W=256, D=16, n_frames=7, wseed=5),
+           'kvnet_256x320_d8': dict(seed=42, H=256, W=320, D=8, n_frames=6, wseed=6)}[name]
+    frames, rng = synth.video(cfg['seed'], cfg['n_frames'], cfg['H'], cfg['W'])
+    exts = synth.camera_track(rng, cfg['n_frames'])
+    sd = arch.synth_state_dict(cfg['wseed'], 64, cfg['D'], 2, 64)
+    d = synth.d_candidates(cfg['D'])
+    return dict(frames=frames, exts=exts, sd=sd, d=d, H=cfg['H'], W=cfg['W'], D=cfg['D'], sigma=10.0,
+                t_win_r=2)
+
+
+KVNET_CASES = ['kvnet_256_d16', 'kvnet_256x320_d8']
+
+
+def window(case, ref_idx):
+    """ref frame [1,3,H,W], src [1,V,3,H,W], poses [1,V,4,4] for the 5-frame window
+    centred on ref_idx (mutils/misc.py:509-517)."""
+    poses, idx = synth.window_rel_poses(case['exts'], ref_idx, case['t_win_r'])
+    ref = case['frames'][ref_idx][None]
+    src = np.stack([case['frames'][i] for i in idx])[None]
+    return ref, src, poses[None]
+
+
+def subsample(a, limit=60000):
+    """Strided view (last two dims) keeping large reference outputs small in the
+    fixtures; the stride is a pure function of the shape so tests can re-derive it."""
+    a = np.asarray(a)
+    step = 1
+    while a.ndim >= 2 and a[..., ::step, ::step].size > limit and step < 16:
+        step += 1
+    return np.ascontiguousarray(a[..., ::step, ::step])
+
+
+def stats(a):
+    a = np.asarray(a, np.float64)
+    fin = np.isfinite(a)
+    return np.array([a[fin].sum(), np.square(a[fin]).sum(), float(fin.sum())], np.float64)
