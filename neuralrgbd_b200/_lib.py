@@ -1,0 +1,70 @@
+"""ctypes binding of libnrgbd.so (include/nrgbd.h). Fails loudly when the library is missing:
+there is no CPU or PyTorch fallback for any entry point."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnrgbd.so')
+
+c_int, c_float, c_ll, c_vp = ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/nrgbd.h one to one.
+SIGNATURES = {
+    'nrgbd_abi_version': (c_int, []),
+    'nrgbd_last_error': (ctypes.c_char_p, []),
+    'nrgbd_launch_count': (c_ll, []),
+    'nrgbd_reset_launch_count': (None, []),
+    'nrgbd_sweep_channel_split': (None, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    'nrgbd_pack_features': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'nrgbd_transpose2d': (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
+    'nrgbd_sweep_workspace_floats': (c_int, [c_int]),
+    'nrgbd_plane_sweep_cost_packed': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_float, c_float, c_int,
+                                              c_vp, c_vp, c_vp]),
+    'nrgbd_warp_to_volume': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp]),
+    'nrgbd_knet_input_volume': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp]),
+    'nrgbd_resample_dpv': (c_int, [c_vp, c_ll, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_float, c_float,
+                                   c_float, c_float, c_float, c_int, c_float, c_float, c_vp, c_ll, c_ll, c_vp]),
+    'nrgbd_dpv_normalize': (c_int, [c_vp, c_vp, c_float, c_int, c_int, c_ll, c_ll, c_vp, c_ll, c_ll, c_vp, c_vp,
+                                    c_vp, c_vp]),
+    'nrgbd_depth_regression': (c_int, [c_vp, c_int, c_int, c_ll, c_ll, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'nrgbd_exp': (c_int, [c_vp, c_ll, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class NrgbdError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libnrgbd.so once. Raises if it has not been built (python -m neuralrgbd_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NrgbdError('libnrgbd.so not found at %s: build it with `python -m neuralrgbd_b200.build` '
+                             '(there is no fallback path)' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)      # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().nrgbd_last_error()
+        raise NrgbdError('nrgbd error %d: %s' % (rc, msg.decode() if msg else ''))
+
+
+def ptr(t):
+    """Device pointer of a CUDA float32 contiguous tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'nrgbd entry points take contiguous CUDA tensors'
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,231 @@
+"""Drop-in mirror of the reference's `warping.homography` hot-path functions.
+
+Same names, positional order, argument meaning (numpy float64 `d_candi`, dict intrinsics,
+list-or-tensor R/t), return shapes/dtypes and error behaviour as
+/root/reference/code/warping/homography.py; every function dispatches to the hand-written
+sm_100a kernels in libnrgbd.so through the C ABI of include/nrgbd.h. torch is used for
+device memory and the current stream only. There is no CPU path: tensors must live on a
+CUDA device and the library must be built.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import ptr, check
+
+_F = ctypes.c_float
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(x):
+    if not x.is_cuda:
+        raise _lib.NrgbdError('neuralrgbd_b200 has no CPU path: expected a CUDA tensor')
+    return x.device
+
+
+_cam_cache = {}
+
+
+def _cam_tensors(cam_intrinsic, device):
+    """K (3x3) and rays (3 x hw) of an intrinsics dict on `device`, cached per dict object."""
+    key = (id(cam_intrinsic), device.index)
+    hit = _cam_cache.get(key)
+    if hit is not None and hit[0] is cam_intrinsic:
+        return hit[1], hit[2]
+    K = torch.as_tensor(cam_intrinsic['intrinsic_M_cuda'], dtype=torch.float32).to(device).contiguous()
+    rays = torch.as_tensor(cam_intrinsic['unit_ray_array_2D'], dtype=torch.float32).to(device).contiguous()
+    if len(_cam_cache) > 64:
+        _cam_cache.clear()
+    _cam_cache[key] = (cam_intrinsic, K, rays)
+    return K, rays
+
+
+def _planes(d_candi, device):
+    # homography.py:311: torch.from_numpy(d_candi.astype(np.float32)).cuda()
+    return torch.from_numpy(np.asarray(d_candi).astype(np.float32)).to(device)
+
+
+def _stack_Rt(R, t, device):
+    if isinstance(R, (list, tuple)):
+        R = torch.stack([torch.as_tensor(r) for r in R])
+        t = torch.stack([torch.as_tensor(x).reshape(3) for x in t])
+    R = R.to(device=device, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
+    t = t.to(device=device, dtype=torch.float32).reshape(-1, 3).contiguous()
+    return R, t
+
+
+def get_rel_extrinsicM(ext_ref, ext_src):
+    ''' Get the extrinisc matrix from ref_view to src_view (homography.py:904-906) '''
+    return ext_src.dot(np.linalg.inv(ext_ref))
+
+
+def img_dis_L2_pard(img0, img1):
+    """homography.py:81-83. Standalone helper kept for API completeness; inside
+    est_swp_volume_v4 this reduction is fused into the sweep kernel."""
+    return torch.sum((img0 - img1) ** 2, 1)
+
+
+def img_dis_L1_pard(img0, img1):
+    """homography.py:85-87 (see img_dis_L2_pard)."""
+    return torch.sum(torch.abs(img0 - img1), 1)
+
+
+def pack_features(x_nchw):
+    """[N,C,h,w] -> (wide [N,hw,Cw] or None, narrow [N,hw,4] or None), the sweep's layouts."""
+    L = _lib.lib()
+    x = x_nchw.contiguous()
+    N, C, h, w = x.shape
+    Cw = C - C % 4
+    Cn = C % 4
+    wide = torch.empty((N, h * w, Cw), device=x.device, dtype=torch.float32) if Cw else None
+    narrow = torch.empty((N, h * w, 4), device=x.device, dtype=torch.float32) if Cn else None
+    check(L.nrgbd_pack_features(ptr(x), C, h * w, N, ptr(wide), ptr(narrow), _stream()))
+    return wide, narrow
+
+
+def est_swp_volume_v4(feat_img_ref, feat_img_src, d_candi, R, t, cam_intrinsic, costV_sigma,
+                      feat_dist='L2', debug_ipdb=False):
+    r'''
+    feat_img_ref - NCHW tensor
+    feat_img_src - NVCHW tensor.  V is for different views
+    R, t - R[idx_view, :, :] - 3x3 rotation matrix
+           t[idx_view, :] - 3x1 transition vector
+    Returns costV [1, D, H, W] (homography.py:293-331).
+    '''
+    if feat_dist not in ('L2', 'L1'):
+        raise Exception('undefined metric for feature distance ...')
+    L = _lib.lib()
+    dev = _dev(feat_img_ref)
+    with torch.cuda.device(dev):
+        H, W, D = feat_img_ref.shape[2], feat_img_ref.shape[3], len(d_candi)
+        C = feat_img_ref.shape[1]
+        V = feat_img_src.shape[1]
+        K, rays = _cam_tensors(cam_intrinsic, dev)
+        dpl = _planes(d_candi, dev)
+        Rs, ts = _stack_Rt(R, t, dev)
+        ref_w, ref_n = pack_features(feat_img_ref.float())
+        src_w, src_n = pack_features(feat_img_src[0].float())
+        cx = float(cam_intrinsic['intrinsic_M'][0, 2]); cy = float(cam_intrinsic['intrinsic_M'][1, 2])
+        ws = torch.empty(L.nrgbd_sweep_workspace_floats(V), device=dev, dtype=torch.float32)
+        cost_hwd = torch.empty((H * W, D), device=dev, dtype=torch.float32)
+        check(L.nrgbd_plane_sweep_cost_packed(ptr(ref_w), ptr(ref_n), ptr(src_w), ptr(src_n), C - C % 4, C % 4,
+                                              V, D, H, W, ptr(K), ptr(Rs), ptr(ts), ptr(rays), ptr(dpl),
+                                              _F(cx), _F(cy), _F(float(costV_sigma)),
+                                              0 if feat_dist == 'L2' else 1, ptr(ws), ptr(cost_hwd), _stream()))
+        costV = torch.empty((1, D, H, W), device=dev, dtype=torch.float32)
+        check(L.nrgbd_transpose2d(ptr(cost_hwd), H * W, D, ptr(costV), _stream()))
+    return costV
+
+
+def _warp_views(feat_img_src, d_candi, R, t, K, rays, cx, cy):
+    L = _lib.lib()
+    is_list = isinstance(R, (list, tuple)) and isinstance(t, (list, tuple))
+    imgs = list(feat_img_src) if is_list else [feat_img_src]
+    dev = _dev(imgs[0])
+    with torch.cuda.device(dev):
+        x = torch.cat([i.float() for i in imgs], dim=0).contiguous()       # [V,C,h,w]
+        V, C, H, W = x.shape
+        D = len(d_candi)
+        dpl = _planes(d_candi, dev)
+        Rs, ts = _stack_Rt(list(R) if is_list else [R], list(t) if is_list else [t], dev)
+        ws = torch.empty(L.nrgbd_sweep_workspace_floats(V), device=dev, dtype=torch.float32)
+        out = torch.empty((V, C, D, H, W), device=dev, dtype=torch.float32)
+        for c0 in range(0, C, 4):
+            cc = min(4, C - c0)
+            chunk = x[:, c0:c0 + cc].contiguous()
+            wide, narrow = pack_features(chunk)          # cc == 4 packs as wide [V,hw,4]: same memory layout
+            packed = narrow if narrow is not None else wide
+            check(L.nrgbd_warp_to_volume(ptr(packed), cc, c0, C, V, D, H, W, ptr(K), ptr(Rs), ptr(ts), ptr(rays),
+                                         ptr(dpl), _F(cx), _F(cy), ptr(ws), ptr(out), _stream()))
+    outs = [out[v] for v in range(V)]
+    return outs if is_list else outs[0]
+
+
+def warp_img_feats_v3(feat_img_src, d_candi, R, t, cam_intrinsic):
+    r'''
+    Warp the feat_imgs_src to the reference view for all candidate depths (homography.py:234-280)
+    feat_img_src - list of source image features (each NCHW, N=1) or one NCHW tensor
+    Returns a list of V tensors C x D x h x w (or one tensor).
+    '''
+    first = feat_img_src[0] if isinstance(feat_img_src, (list, tuple)) else feat_img_src
+    K, rays = _cam_tensors(cam_intrinsic, _dev(first))
+    cx = float(cam_intrinsic['intrinsic_M'][0, 2]); cy = float(cam_intrinsic['intrinsic_M'][1, 2])
+    return _warp_views(feat_img_src, d_candi, R, t, K, rays, cx, cy)
+
+
+def warp_img_feats_mgpu(feat_img_src, d_candi, R, t, IntM_tensors, unit_ray_arrays_2D):
+    r'''homography.py:183-232: intrinsics arrive as stacked tensors (1x3x3, 1x3xhw) scattered by
+    DataParallel; u/v centre are IntM[0,2], IntM[1,2].'''
+    first = feat_img_src[0] if isinstance(feat_img_src, (list, tuple)) else feat_img_src
+    dev = _dev(first)
+    K = IntM_tensors.squeeze(0).to(device=dev, dtype=torch.float32).contiguous()
+    rays = unit_ray_arrays_2D.squeeze(0).to(device=dev, dtype=torch.float32).contiguous()
+    Kh = K.cpu()
+    return _warp_views(feat_img_src, d_candi, R, t, K, rays, float(Kh[0, 2]), float(Kh[1, 2]))
+
+
+def _set_vol_border(vol, border_val):
+    '''homography.py:873-887 (clone + six face fills). Standalone helper; resample_vol_cuda
+    applies the same overwrite inside its kernel without materialising the copy.'''
+    vol_ = vol + 0.
+    vol_[:, :, 0, :, :] = border_val
+    vol_[:, :, :, 0, :] = border_val
+    vol_[:, :, :, :, 0] = border_val
+    vol_[:, :, -1, :, :] = border_val
+    vol_[:, :, :, -1, :] = border_val
+    vol_[:, :, :, :, -1] = border_val
+    return vol_
+
+
+def resample_params(cam_intrinsic, d_candi, d_candi_new=None):
+    """(d_pts float32 ndarray, tan_hh, tan_hv, z_half, z_radius) per homography.py:668-696."""
+    hhfov = math.radians(cam_intrinsic['hfov']) * .5
+    hvfov = math.radians(cam_intrinsic['vfov']) * .5
+    d_ = d_candi_new if d_candi_new is not None else d_candi
+    d_pts = np.asarray(d_).astype(np.float32)
+    if d_candi_new is not None:
+        z_max, z_min = np.max(d_candi), np.min(d_candi)          # float64, as numpy scalars (:687)
+        z_half = np.float32((z_max + z_min) * .5)
+        z_radius = np.float32((z_max - z_min) * .5)
+    else:
+        z_max, z_min = np.float32(d_pts.max()), np.float32(d_pts.min())   # point-cloud z = f32(d)*1 (:689-690)
+        z_half = np.float32((z_max + z_min) * np.float32(.5))
+        z_radius = np.float32((z_max - z_min) * np.float32(.5))
+    return d_pts, np.float32(math.tan(hhfov)), np.float32(math.tan(hvfov)), z_half, z_radius
+
+
+def resample_vol_cuda(src_vol, rel_extM, cam_intrinsic=None, d_candi=None, d_candi_new=None,
+                      padding_value=0., output_tensor=False, is_debug=False,
+                      PointsDs_ref_cam_coord_in=None, clamp=None):
+    r'''
+    homography.py:654-723. src_vol [1,D,H,W]; rel_extM 4x4 tensor; returns [D,H,W].
+    if d_candi_new is not None:
+    d_candi : candidate depth values for the src view;
+    d_candi_new : candidate depth values for the ref view.
+    `clamp=(lo, hi)` (extension) fuses the clamp of test_utils/test_KVNet.py:58-59.
+    '''
+    assert d_candi is not None, 'd_candi should be some np.array object'
+    if PointsDs_ref_cam_coord_in is not None or is_debug:
+        raise _lib.NrgbdError('resample_vol_cuda: PointsDs_ref_cam_coord_in / is_debug are not supported '
+                              '(the point cloud is never materialised)')
+    L = _lib.lib()
+    dev = _dev(src_vol)
+    with torch.cuda.device(dev):
+        N, D, H, W = src_vol.shape
+        K, rays = _cam_tensors(cam_intrinsic, dev)
+        d_pts, tan_hh, tan_hv, z_half, z_radius = resample_params(cam_intrinsic, d_candi, d_candi_new)
+        dp = torch.from_numpy(d_pts).to(dev)
+        E = rel_extM.to(device=dev, dtype=torch.float32).contiguous()
+        vol = src_vol.float().contiguous()
+        out = torch.empty((D, H, W), device=dev, dtype=torch.float32)
+        lo, hi = (clamp if clamp is not None else (0., 0.))
+        check(L.nrgbd_resample_dpv(ptr(vol), H * W, 1, ptr(E), ptr(rays), ptr(dp), D, H, W, _F(tan_hh), _F(tan_hv),
+                                   _F(z_half), _F(z_radius), _F(float(padding_value)), 1 if clamp is not None else 0,
+                                   _F(lo), _F(hi), ptr(out), H * W, 1, _stream()))
+    return out

@@ -1,0 +1,92 @@
+"""Micro-benchmarks of the geometry kernels at the BASELINE metric shape (development aid; the
+judged numbers come from bench.py). CUDA events on the current stream, L2 flushed between
+iterations by writing a 256 MB buffer."""
+import ctypes
+import json
+import sys
+import os
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neuralrgbd_b200 import _lib, synth           # noqa: E402
+from neuralrgbd_b200._lib import ptr, check       # noqa: E402
+import neuralrgbd_b200.warping.homography as H    # noqa: E402
+
+dev = torch.device('cuda:0')
+L = _lib.lib()
+F = ctypes.c_float
+st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)     # noqa: E731
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    h, w, C, V, D = 120, 160, 67, 4, 64
+    if len(sys.argv) > 1:
+        h, w, C, V, D = [int(x) for x in sys.argv[1:6]]
+    hw = h * w
+    rng = np.random.RandomState(0)
+    Cw, Cn = C - C % 4, C % 4
+    ref_w = torch.randn(hw, Cw, device=dev); src_w = torch.randn(V, hw, Cw, device=dev)
+    ref_n = torch.randn(hw, 4, device=dev); src_n = torch.randn(V, hw, 4, device=dev)
+    exts = synth.camera_track(rng, V + 1)
+    poses, _ = synth.window_rel_poses(exts, V // 2, V // 2)
+    R = torch.from_numpy(np.ascontiguousarray(poses[:, :3, :3])).to(dev); t = torch.from_numpy(np.ascontiguousarray(poses[:, :3, 3])).to(dev)
+    fx = (w / 2) / np.tan(np.arctan(320 / 585.)); fy = (h / 2) / np.tan(np.arctan(240 / 585.))
+    K = torch.tensor([[fx, 0, w / 2], [0, fy, h / 2], [0, 0, 1]], dtype=torch.float32, device=dev)
+    xs = (np.arange(w) + .5) / w * 2 - 1; ys = (np.arange(h) + .5) / h * 2 - 1
+    rays = np.stack([np.tile(320 / 585. * xs[None], (h, 1)), np.tile(240 / 585. * ys[:, None], (1, w)), np.ones((h, w))]).reshape(3, -1)
+    rays = torch.from_numpy(rays.astype(np.float32)).to(dev)
+    dpl = torch.from_numpy(synth.d_candidates(D).astype(np.float32)).to(dev)
+    ws = torch.empty(V * 12, device=dev); cost = torch.empty(hw, D, device=dev)
+
+    def sweep():
+        check(L.nrgbd_plane_sweep_cost_packed(ptr(ref_w) if Cw else None, ptr(ref_n) if Cn else None,
+                                              ptr(src_w) if Cw else None, ptr(src_n) if Cn else None, Cw, Cn, V, D, h, w,
+                                              ptr(K), ptr(R), ptr(t), ptr(rays), ptr(dpl), F(w / 2), F(h / 2), F(10.), 0,
+                                              ptr(ws), ptr(cost), st()))
+    res = {}
+    med, mn = timeit(sweep)
+    alg = (1 + V) * C * hw * 4 + D * hw * 4 + 3 * hw * 4
+    res['sweep'] = dict(us_med=med, us_min=mn, alg_MB=alg / 1e6, GBps=alg / med / 1e3,
+                        gflops=V * D * hw * (11 * C + 30) / med / 1e3)
+    bv = torch.log_softmax(-cost, 1).contiguous(); out = torch.empty_like(bv)
+    dep = torch.empty(hw, device=dev); conf = torch.empty(hw, device=dev)
+
+    def norm():
+        check(L.nrgbd_dpv_normalize(ptr(cost), None, F(-1.), hw, D, 1, D, ptr(out), 1, D, ptr(dpl), ptr(dep), ptr(conf), st()))
+    med, mn = timeit(norm)
+    res['dpv_normalize_hwd'] = dict(us_med=med, us_min=mn, GBps=2 * hw * D * 4 / med / 1e3)
+    E = torch.from_numpy(np.linalg.inv(poses[V // 2].astype(np.float64)).astype(np.float32)).to(dev)
+    vol = bv.t().contiguous(); outv = torch.empty_like(vol)
+
+    def resample():
+        check(L.nrgbd_resample_dpv(ptr(vol), hw, 1, ptr(E), ptr(rays), ptr(dpl), D, h, w, F(320 / 585.), F(240 / 585.),
+                                   F(2.55), F(2.45), F(-4.16), 1, F(-1000.), F(0.), ptr(outv), hw, 1, st()))
+    med, mn = timeit(resample)
+    res['resample_dhw'] = dict(us_med=med, us_min=mn, GBps=2 * hw * D * 4 / med / 1e3)
+    rgb = torch.randn(V, hw, 4, device=dev); outw = torch.empty(V, 3, D, hw, device=dev)
+
+    def warp():
+        check(L.nrgbd_warp_to_volume(ptr(rgb), 3, 0, 3, V, D, h, w, ptr(K), ptr(R), ptr(t), ptr(rays), ptr(dpl), F(w / 2),
+                                     F(h / 2), ptr(ws), ptr(outw), st()))
+    med, mn = timeit(warp)
+    res['warp_to_volume'] = dict(us_med=med, us_min=mn, GBps=V * (3 * hw + 3 * D * hw) * 4 / med / 1e3)
+    print(json.dumps(dict(shape=dict(h=h, w=w, C=C, V=V, D=D), kernels=res), indent=1))
+
+
+if __name__ == '__main__':
+    main()
