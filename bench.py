@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - depth frames/s of the plane-sweep DPV hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] - ScanNet-shaped 640x480 frames, 64 depth
+planes, 4 source views, D-Net DPV (feature CNN + fused plane sweep + log-softmax) + R-Net
+up-sampling = the first-window branch of KVNET.forward (models/KVNET.py:93-143), i.e. SURVEY
+§8(d) config C2. One step = one depth frame. Synthetic seeded frames / poses / random-init
+weights of the reference architecture (no datasets or checkpoints offline).
+
+value  : whole-job frames/s with the window already resident in HBM (engine C ABI, device ptrs).
+e2e    : the same metric through the public Python surface (KVNET.forward + depth regression)
+         with pinned HOST buffers: H2D of the 5-frame window + poses and D2H of the full-resolution
+         expected-depth and confidence maps inside the timed region, every step.
+roofline: the conv implicit-GEMM kernels (dominant: >95 % of the step) timed live with CUDA events on the
+         launching stream during the timed region; algorithmic FLOPs / time against the measured
+         bf16 tensor peak of MEASURED_PEAKS.json (these kernels are exact-fp32 CUDA-core FFMA; the
+         fraction shows the head-room a tcgen05 3xTF32 path has). The fused plane-sweep
+         kernel's HBM fraction is reported beside it (config.sweep).
+cpu_baseline / --impl reference: oracle/torch_port.py, the CPU torch port of the reference's path (same ATen
+         ops; the reference itself cannot travel to the GPU box), on all host cores.
+
+N > 1 (torchrun): one process per GPU, frames shard naturally (independent windows), weights are
+broadcast once over NCCL, no per-frame collective; value = N*K frames / max-over-ranks time.
+"""
+import argparse
+import contextlib
+import ctypes
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_IMG, W_IMG, D_PLANES, V_SRC = 480, 640, 64, 4
+WORKLOAD = 'scannet640x480_d64_v4_dnet_dpv_plus_rnet (BASELINE.json configs[1]; SURVEY C2)'
+
+
+def read_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j['hbm_gbs'], bf16=j['bf16_tflops'], bf16_sustained=j.get('bf16_tflops_sustained', j['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop = False
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if self.rows[0][1].replace('.', '').isdigit() else None,
+                'samples': len(self.rows), 'reasons': sorted(reasons)}
+
+
+def make_windows(n_windows, seed=7):
+    """n_windows seeded 5-frame windows: frames [V+1,3,H,W] (sources then reference, basic.py:245) and
+    relative poses [V,4,4]."""
+    from neuralrgbd_b200 import synth
+    frames, rng = synth.video(seed, n_windows + 4, H_IMG, W_IMG)
+    exts = synth.camera_track(rng, n_windows + 4)
+    wins = []
+    for i in range(n_windows):
+        poses, idx = synth.window_rel_poses(exts, 2 + i, 2)
+        f = np.stack([frames[j] for j in idx] + [frames[2 + i]])
+        wins.append((np.ascontiguousarray(f, np.float32), np.ascontiguousarray(poses, np.float32)))
+    return wins
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_frame_seconds(n_frames=1):
+    """Time the CPU torch port of the reference path (oracle/torch_port.py: the same ATen ops in the
+    same order as the reference, bit-identical to its recorded outputs) on whole depth frames of the
+    bench workload (same shapes, seeded inputs and weights), all host threads."""
+    import torch
+    from oracle import planesweep_oracle as O, torch_port as TP
+    from neuralrgbd_b200 import arch, synth
+    torch.set_num_threads(os.cpu_count())
+    cam = O.make_cam_intrinsics(585., 585., 320., 240., [W_IMG // 4, H_IMG // 4])
+    sd = TP._P(arch.synth_state_dict(5, 64, D_PLANES, 2, 64))
+    d = synth.d_candidates(D_PLANES)
+    wins = make_windows(n_frames)
+    ts = []
+    for f, poses in wins:
+        t0 = time.perf_counter()
+        ref, bv, dep = TP.kvnet_first_window(sd, f[-1:], f[None, :-1], poses[None], cam, d, 10.)
+        ts.append(time.perf_counter() - t0)
+        assert np.isfinite(dep).all()
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    n_warm = 1 if args.warmup > 0 else 0
+    n = max(1, min(args.steps, 3))           # bounded: each frame costs seconds of CPU time
+    ts = cpu_frame_seconds(n_warm + n)[n_warm:]
+    sec = float(np.mean(ts))
+    val = 1.0 / sec
+    line = {
+        'impl': 'reference', 'metric': 'depth frames/sec at 640x480x64-plane x4-view', 'value': val, 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': len(ts), 'warmup': n_warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG]},
+        'cpu_baseline': {'value': val, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': 'CPU torch port of the reference path (same ATen ops, bit-identical to the reference fixtures), '
+                                   '%d whole 640x480 frame(s) after %d warm-up, torch.set_num_threads(%d)' % (len(ts), n_warm, cores)},
+        'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# the engine arm
+# ----------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from neuralrgbd_b200 import _lib, arch, camera, synth
+    from neuralrgbd_b200._lib import ptr, check
+    from neuralrgbd_b200.models.KVNET import KVNET
+    from neuralrgbd_b200.mutils import misc
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+    peaks = read_peaks()
+    K, Wm = args.steps, args.warmup
+
+    cam = camera.make_cam_intrinsics(585., 585., 320., 240., [W_IMG // 4, H_IMG // 4])
+    d = synth.d_candidates(D_PLANES)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = KVNET(64, cam, d, 10., 64, None, t_win_r=2)
+    # random-init weights of the reference architecture: rank 0 generates, NCCL broadcasts (weights only)
+    if rank == 0:
+        sd = arch.synth_state_dict(5, 64, D_PLANES, 2, 64)
+        model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model = model.to(dev)
+    if world > 1:
+        for t in list(model.parameters()) + [b for b in model.buffers() if b.dtype == torch.float32]:
+            dist.broadcast(t.data, src=0)
+
+    n_win = 4
+    wins = make_windows(n_win, seed=7 + rank)           # every rank owns its own windows (frames shard naturally)
+    dev_frames = [torch.from_numpy(f).to(dev) for f, _ in wins]
+    dev_poses = [torch.from_numpy(p).to(dev) for _, p in wins]
+    pin_frames = [torch.from_numpy(f).pin_memory() for f, _ in wins]
+    pin_poses = [torch.from_numpy(p).pin_memory() for _, p in wins]
+    h2d_bytes = pin_frames[0].numel() * 4 + pin_poses[0].numel() * 4
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    out_ref = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
+    out_bv = torch.empty((D_PLANES, H_IMG // 4, W_IMG // 4), device=dev)
+    out_dep = torch.empty((H_IMG // 4, W_IMG // 4), device=dev)
+    host_depth = torch.empty((1, H_IMG, W_IMG)).pin_memory()
+    host_conf = torch.empty((1, H_IMG, W_IMG)).pin_memory()
+    d2h_bytes = host_depth.numel() * 4 + host_conf.numel() * 4
+
+    # one API-level call creates the engine, syncs weights and the camera
+    with torch.no_grad():
+        model(dev_frames[0][-1:], dev_frames[0][None, :-1], dev_poses[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+    ent = model._engine(H_IMG, W_IMG, V_SRC, dev)
+    hnd = ent['h']
+    stream = torch.cuda.current_stream()
+    st = ctypes.c_void_p(stream.cuda_stream)
+
+    def step_resident(i):
+        flush.zero_()
+        check(L.nrgbd_kvnet_forward(hnd, ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(out_ref), None,
+                                    ptr(out_bv), None, ptr(out_dep), None, st))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM ----------------
+    for i in range(Wm):
+        step_resident(i)
+    check(L.nrgbd_kvnet_set_option(hnd, b'profile', 1))
+    ms_c, wk_c, n_c = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))   # clear
+    L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    L.nrgbd_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        step_resident(Wm + i)
+    e1.record(stream)
+    barrier()
+    launches = int(L.nrgbd_launch_count())
+    ms_total = e0.elapsed_time(e1)
+    sampler.stop = True
+    check(L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
+    conv_ms, conv_flops, conv_n = ms_c.value, wk_c.value, n_c.value
+    check(L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
+    sw_ms, sw_bytes, sw_n = ms_c.value, wk_c.value, n_c.value
+    check(L.nrgbd_kvnet_set_option(hnd, b'profile', 0))
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K / (ms_max * 1e-3)
+
+    # ---------------- e2e: public Python surface, pinned host buffers ----------------
+    def step_e2e(i):
+        flush.zero_()
+        f = pin_frames[i % n_win].to(dev, non_blocking=True)
+        p = pin_poses[i % n_win].to(dev, non_blocking=True)
+        with torch.no_grad():
+            out = model(f[-1:], f[None, :-1], p[None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+            dep, conf = misc.depth_val_regression(out[0], d, BV_log=True, return_conf=True)
+        host_depth.copy_(dep, non_blocking=True)
+        host_conf.copy_(conf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the user reads the depth map on the host
+    for i in range(Wm):
+        step_e2e(i)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        step_e2e(Wm + i)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / (float(t.item()) * 1e-3)
+    assert np.isfinite(host_depth.numpy()).all()
+
+    if rank == 0:
+        conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        sweep_gbs = sw_bytes / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
+        peak_tf = peaks['bf16_sustained']       # kernels timed inside a long step -> sustained figure
+        line = {
+            'metric': 'depth frames/sec at 640x480x64-plane x4-view', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+            'steps': K, 'warmup': Wm, 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG], 'parallelism': 'dp%d (frames sharded, weights NCCL-broadcast once)' % world,
+                       'l2': 'explicit 256 MiB flush write before every step (inside the timed region)',
+                       'weights': 'random init of the reference architecture (arch.synth_state_dict seed 5)',
+                       'sweep': {'avg_us': 1e3 * sw_ms / max(sw_n, 1), 'algorithmic_GBps': sweep_gbs, 'frac_of_hbm_peak': sweep_gbs / peaks['hbm_gbs'],
+                                 'note': 'fused plane-sweep cost kernel incl. setup launch; C=67 is L1/FFMA bound, not HBM bound (SURVEY 8d)'},
+                       'conv_share_of_step': conv_ms / ms_total if ms_total > 0 else None},
+            'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
+            'gpu_launches': launches,
+            'clocks': sampler.summary(),
+            'roofline': {'bound': 'tensor', 'achieved': conv_tflops, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': conv_tflops / peak_tf,
+                         'traffic': None, 'kernel': 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM, %d launches/step, avg %.1f us)' % (conv_n // max(K, 1), 1e3 * conv_ms / max(conv_n, 1)),
+                         'peak_source': peaks['source'] + ', sustained bf16'},
+        }
+        # cpu baseline: bounded sample of the same workload through the oracle port (rank 0, N = 1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            ts = cpu_frame_seconds(2)[1:]
+            line['cpu_baseline'] = {'value': 1.0 / float(np.mean(ts)), 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                    'sample': 'CPU torch port of the reference path (same ATen ops, bit-identical to the reference '
+                                              'fixtures), 1 whole 640x480 frame after 1 warm-up frame, torch.set_num_threads(%d)' % os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'engine' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

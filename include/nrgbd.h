@@ -96,16 +96,91 @@ int nrgbd_resample_dpv(const float* vol, long long in_stride_d, long long in_str
  *   sign=-1, b=NULL : BV = log_softmax(-costV)            models/basic.py:299-300
  *   sign=+1, b=prior: DPV = log_softmax(gain + BV_predict) models/KVNET.py:172-173
  * with d_planes also depth[pix] = sum_d exp(out)*d (mutils/misc.py:532-548) and
- * conf[pix] = max_d exp(out) (test_utils/export_res.py:55-62). out may be NULL. */
-int nrgbd_dpv_normalize(const float* a, const float* b, float sign, int n_pix, int D, long long in_sd,
-                        long long in_sp, float* out, long long out_sd, long long out_sp,
-                        const float* d_planes, float* depth, float* conf, nrgbd_stream_t stream);
+ * conf[pix] = max_d exp(out) (test_utils/export_res.py:55-62). out may be NULL.
+ * Element (d,pix) of a / b / out lives at d*_sd + pix*_sp of the respective array. */
+int nrgbd_dpv_normalize(const float* a, long long in_sd, long long in_sp, const float* b, long long b_sd,
+                        long long b_sp, float sign, int n_pix, int D, float* out, long long out_sd,
+                        long long out_sp, const float* d_planes, float* depth, float* conf,
+                        nrgbd_stream_t stream);
 /* depth[pix] = sum_d (bv_log ? exp(bv) : bv)(d,pix) * d_planes[d]  -- mutils/misc.py:532-548
  * depth_val_regression (no normalisation); conf[pix] = max_d of the same probability. */
 int nrgbd_depth_regression(const float* bv, int n_pix, int D, long long in_sd, long long in_sp,
                            const float* d_planes, int bv_log, float* depth, float* conf,
                            nrgbd_stream_t stream);
 int nrgbd_exp(const float* x, long long n, float* y, nrgbd_stream_t stream);
+
+/* ---- a5, a8, a10: conv stacks (channels-last fp32, channel stride Cs % 4 == 0) ---------------
+ * Replace nn.Conv2d/Conv3d/ConvTranspose2d (+bias, +LeakyReLU) and training-mode BatchNorm
+ * (models/psm_submodule.py:10-23, models/basic.py:71-94, models/Refine.py:47-77,
+ * models/m_submodule.py:18-43). */
+/* PyTorch weight [Cout][Cin][taps] (transposed=0) or [Cin][Cout][taps] (transposed=1) ->
+ * packed [taps][Cin_pad][Cout_pad], zero padded. */
+int nrgbd_pack_conv_weight(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad,
+                           int Cout_pad, float* out, nrgbd_stream_t stream);
+/* x [N][Din][Hin][Win][Cs_in] -> y [N][Din][Hout][Wout][Cs_out] channels [c_off, c_off+Cout);
+ * kd x kh x kw taps (kd=1: 2-D; depth stride 1, pad kd/2). stats: [2][Cout] doubles accumulated
+ * (sum, sum of squares of the stored outputs) for BatchNorm, or NULL. */
+int nrgbd_conv_nhwc(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in,
+                    const float* w, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw,
+                    int stride, int pad, int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off,
+                    int leaky, double* stats, nrgbd_stream_t stream);
+/* nn.ConvTranspose2d(kernel 4, stride 2, padding 1); w packed [16][Cin_pad][Cout_pad]. */
+int nrgbd_conv_transpose2d_k4s2_nhwc(const float* x, int N, int Hin, int Win, int Cin_pad, int Cs_in,
+                                     const float* w, const float* bias, int Cout, int Cout_pad, float* y,
+                                     int Cs_out, int c_off, int leaky, nrgbd_stream_t stream);
+/* scale = gamma/sqrt(var+eps), shift = beta - mean*scale from accumulated stats (biased variance);
+ * run_mean/run_var (may be NULL) get the training-mode momentum update. */
+int nrgbd_bn_finalize(const double* stats, int C, double count, const float* gamma, const float* beta,
+                      float eps, float* scale, float* shift, float* run_mean, float* run_var,
+                      float momentum, nrgbd_stream_t stream);
+/* y = [relu](x*scale + shift) [+ res] over n_pos positions of Cs channels (C logical). */
+int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const float* res, int relu,
+                   long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);
+/* layout / pooling helpers (P = positions per image) */
+int nrgbd_nchw_to_nhwc(const float* x, int N, int C, long long P, float* y, int Cs, int c_off,
+                       nrgbd_stream_t stream);
+int nrgbd_nhwc_to_nchw(const float* x, int N, int C, long long P, int Cs, int c_off, float* y,
+                       nrgbd_stream_t stream);
+int nrgbd_avgpool_nhwc(const float* x, int N, int H, int W, int Cs_in, int C, int k, float* y, int Cs_out,
+                       int c_off, nrgbd_stream_t stream);
+int nrgbd_upsample_bilinear_ac_nhwc(const float* x, int N, int Hi, int Wi, int Cs_in, int C, float* y,
+                                    int Ho, int Wo, int Cs_out, int c_off, nrgbd_stream_t stream);
+/* y[p][c_off_out + c] = op(x[p][c_off_in + c]), op 0 = copy, 1 = exp */
+int nrgbd_copy_channels(const float* x, long long P, int Cs_in, int c_off_in, int C, int op, float* y,
+                        int Cs_out, int c_off_out, nrgbd_stream_t stream);
+
+/* ---- a4, a6: whole-frame engine -------------------------------------------------------------
+ * replaces models/KVNET.py:35-185 (KVNET.__init__/forward with if_refined=True, refineNet_name='DPV')
+ * + models/basic.py:223-323 (D_NET_BASIC.forward) + the DPV propagation of
+ * test_utils/test_KVNet.py:46-59. The layer plan, buffer pool, packed weights and camera tables live
+ * in the opaque engine; one call runs one depth frame on `stream`. */
+typedef struct nrgbd_kvnet nrgbd_kvnet;
+int nrgbd_kvnet_create(int H, int W, int D, int V, int feature_dim, int kv_feature_dim, float sigma,
+                       int metric, nrgbd_kvnet** out);
+int nrgbd_kvnet_destroy(nrgbd_kvnet* e);
+/* name = reference state_dict key (a leading "module." and the d_net.feature_extraction alias are
+ * folded); is_device: borrow a device pointer, else copy a host array. */
+int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, long long n, int is_device);
+/* slot 0: intrinsics captured at construction (D-Net); slot 1: per-call intrinsics (K-Net warp,
+ * propagation). Host arrays: K 3x3, rays 3 x (H/4*W/4); fovs in degrees (cam_intrinsic dict). */
+int nrgbd_kvnet_set_camera(nrgbd_kvnet* e, int slot, const float* K_host, const float* rays_host, float cx,
+                           float cy, double hfov_deg, double vfov_deg);
+int nrgbd_kvnet_set_planes(nrgbd_kvnet* e, const float* d_host, int D);   /* float32(d_candi) */
+int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value);   /* "bn_update_running", "profile" */
+/* with option "profile"=1 the engine brackets its conv (category 0, work = flops) and plane-sweep
+ * (category 1, work = algorithmic bytes) launches with CUDA events; this returns and clears the sums. */
+int nrgbd_kvnet_profile_read(nrgbd_kvnet* e, int category, double* ms, double* work, long long* launches);
+long long nrgbd_kvnet_workspace_bytes(nrgbd_kvnet* e);
+/* frames [V+1][3][H][W] (sources then reference), poses [V][4][4], bv_predict [D][h][w] or NULL
+ * (first window). Outputs (any may be NULL): dmap_cur_refined, dmap_refined [D][H][W] log-DPV;
+ * bv_cur, dpv [D][h][w] log-DPV; depth_lowres, conf_lowres [h][w]. All device pointers. */
+int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses, const float* bv_predict,
+                        float* dmap_cur_refined, float* dmap_refined, float* bv_cur, float* dpv,
+                        float* depth_lowres, float* conf_lowres, nrgbd_stream_t stream);
+/* out [D][h][w] = clamp(resample(dpv, rel_pose_inv, pad = log(1/D)), -1000, 0); dpv_dhw NULL = the
+ * engine's own DPV of the last forward. */
+int nrgbd_kvnet_propagate(nrgbd_kvnet* e, const float* dpv_dhw, const float* rel_pose_inv_dev, float* out_dhw,
+                          nrgbd_stream_t stream);
 
 #ifdef __cplusplus
 }

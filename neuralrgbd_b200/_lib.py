@@ -27,10 +27,36 @@ SIGNATURES = {
                                         c_vp, c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp]),
     'nrgbd_resample_dpv': (c_int, [c_vp, c_ll, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_float, c_float,
                                    c_float, c_float, c_float, c_int, c_float, c_float, c_vp, c_ll, c_ll, c_vp]),
-    'nrgbd_dpv_normalize': (c_int, [c_vp, c_vp, c_float, c_int, c_int, c_ll, c_ll, c_vp, c_ll, c_ll, c_vp, c_vp,
-                                    c_vp, c_vp]),
+    'nrgbd_dpv_normalize': (c_int, [c_vp, c_ll, c_ll, c_vp, c_ll, c_ll, c_float, c_int, c_int, c_vp, c_ll, c_ll,
+                                    c_vp, c_vp, c_vp, c_vp]),
     'nrgbd_depth_regression': (c_int, [c_vp, c_int, c_int, c_ll, c_ll, c_vp, c_int, c_vp, c_vp, c_vp]),
     'nrgbd_exp': (c_int, [c_vp, c_ll, c_vp, c_vp]),
+    'nrgbd_pack_conv_weight': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'nrgbd_conv_nhwc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp,
+                                c_vp]),
+    'nrgbd_conv_transpose2d_k4s2_nhwc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int,
+                                                 c_vp, c_int, c_int, c_int, c_vp]),
+    'nrgbd_bn_finalize': (c_int, [c_vp, c_int, ctypes.c_double, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp,
+                                  c_float, c_vp]),
+    'nrgbd_bn_apply': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp]),
+    'nrgbd_nchw_to_nhwc': (c_int, [c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int, c_vp]),
+    'nrgbd_nhwc_to_nchw': (c_int, [c_vp, c_int, c_int, c_ll, c_int, c_int, c_vp, c_vp]),
+    'nrgbd_avgpool_nhwc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    'nrgbd_upsample_bilinear_ac_nhwc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int,
+                                                c_int, c_vp]),
+    'nrgbd_copy_channels': (c_int, [c_vp, c_ll, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    'nrgbd_kvnet_create': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, ctypes.POINTER(c_vp)]),
+    'nrgbd_kvnet_destroy': (c_int, [c_vp]),
+    'nrgbd_kvnet_set_param': (c_int, [c_vp, ctypes.c_char_p, c_vp, c_ll, c_int]),
+    'nrgbd_kvnet_set_camera': (c_int, [c_vp, c_int, c_vp, c_vp, c_float, c_float, ctypes.c_double, ctypes.c_double]),
+    'nrgbd_kvnet_set_planes': (c_int, [c_vp, c_vp, c_int]),
+    'nrgbd_kvnet_set_option': (c_int, [c_vp, ctypes.c_char_p, c_int]),
+    'nrgbd_kvnet_workspace_bytes': (c_ll, [c_vp]),
+    'nrgbd_kvnet_profile_read': (c_int, [c_vp, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(c_ll)]),
+    'nrgbd_kvnet_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'nrgbd_kvnet_propagate': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,129 @@
+"""Op-level host wrappers of the conv-stack entry points (nrgbd_conv_nhwc & co.) taking and
+returning NCHW / NCDHW torch tensors. Used by the parity tests to exercise each kernel in
+isolation; the engine calls the same C entry points directly from C++."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ptr, check
+
+_F = ctypes.c_float
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pad4(c):
+    return (c + 3) // 4 * 4
+
+
+def to_cl(x):
+    """[N,C,(D,)H,W] -> channels-last [N,(D,)H,W,Cs] with zero pad channels."""
+    L = _lib.lib()
+    N, C = x.shape[0], x.shape[1]
+    P = 1
+    for s in x.shape[2:]:
+        P *= s
+    Cs = pad4(C)
+    y = torch.zeros((N,) + tuple(x.shape[2:]) + (Cs,), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_nchw_to_nhwc(ptr(x.float().contiguous()), N, C, P, ptr(y), Cs, 0, _st()))
+    return y
+
+
+def from_cl(y, C):
+    L = _lib.lib()
+    N = y.shape[0]; Cs = y.shape[-1]
+    sp = tuple(y.shape[1:-1])
+    P = 1
+    for s in sp:
+        P *= s
+    x = torch.empty((N, C) + sp, device=y.device, dtype=torch.float32)
+    check(L.nrgbd_nhwc_to_nchw(ptr(y.contiguous()), N, C, P, Cs, 0, ptr(x), _st()))
+    return x
+
+
+def pack_weight(w, transposed=False):
+    L = _lib.lib()
+    if transposed:
+        Cin, Cout = w.shape[0], w.shape[1]
+    else:
+        Cout, Cin = w.shape[0], w.shape[1]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    out = torch.empty((taps, pad4(Cin), pad4(Cout)), device=w.device, dtype=torch.float32)
+    check(L.nrgbd_pack_conv_weight(ptr(w.float().contiguous()), 1 if transposed else 0, Cout, Cin, taps, pad4(Cin),
+                                   pad4(Cout), ptr(out), _st()))
+    return out
+
+
+def conv(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stats=False):
+    """nn.Conv2d / nn.Conv3d(3x3x3, pad 1) forward on NCHW/NCDHW input. Returns y (same rank) and
+    optionally the [2, Cout] float64 (sum, sum of squares) statistics."""
+    L = _lib.lib()
+    is3d = x.dim() == 5
+    xc = to_cl(x)
+    N = x.shape[0]
+    Din = x.shape[2] if is3d else 1
+    Hin, Win = x.shape[-2], x.shape[-1]
+    Cout, Cin = w.shape[0], w.shape[1]
+    kd = w.shape[2] if is3d else 1
+    kh, kw = w.shape[-2], w.shape[-1]
+    Ho = (Hin + 2 * pad - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (Win + 2 * pad - dilation * (kw - 1) - 1) // stride + 1
+    wp = pack_weight(w)
+    y = torch.zeros((N,) + ((Din,) if is3d else ()) + (Ho, Wo, pad4(Cout)), device=x.device, dtype=torch.float32)
+    stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float64) if want_stats else None
+    check(L.nrgbd_conv_nhwc(ptr(xc), N, Din, Hin, Win, pad4(Cin), xc.shape[-1], ptr(wp), ptr(bias), Cout, pad4(Cout), kd,
+                            kh, kw, stride, pad, dilation, ptr(y), Ho, Wo, pad4(Cout), 0, 1 if leaky else 0,
+                            ctypes.c_void_p(stats.data_ptr()) if want_stats else None, _st()))
+    out = from_cl(y, Cout)
+    return (out, stats) if want_stats else out
+
+
+def conv_transpose2d(x, w, bias=None, leaky=False):
+    """nn.ConvTranspose2d(kernel 4, stride 2, padding 1) forward on NCHW input."""
+    L = _lib.lib()
+    xc = to_cl(x)
+    N, Cin, Hin, Win = x.shape
+    Cout = w.shape[1]
+    wp = pack_weight(w, transposed=True)
+    y = torch.zeros((N, 2 * Hin, 2 * Win, pad4(Cout)), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_conv_transpose2d_k4s2_nhwc(ptr(xc), N, Hin, Win, pad4(Cin), xc.shape[-1], ptr(wp), ptr(bias), Cout,
+                                             pad4(Cout), ptr(y), pad4(Cout), 0, 1 if leaky else 0, _st()))
+    return from_cl(y, Cout)
+
+
+def batch_norm(x, stats, gamma, beta, relu=False, residual=None, eps=1e-5):
+    """Training-mode BatchNorm from accumulated statistics, optional ReLU / residual add."""
+    L = _lib.lib()
+    C = x.shape[1]
+    xc = to_cl(x)
+    n_pos = xc.numel() // xc.shape[-1]
+    scale = torch.empty(C, device=x.device); shift = torch.empty(C, device=x.device)
+    check(L.nrgbd_bn_finalize(ctypes.c_void_p(stats.data_ptr()), C, float(n_pos), ptr(gamma), ptr(beta), _F(eps), ptr(scale),
+                              ptr(shift), None, None, _F(0.1), _st()))
+    rc = to_cl(residual) if residual is not None else None
+    check(L.nrgbd_bn_apply(ptr(xc), ptr(scale), ptr(shift), ptr(rc), 1 if relu else 0, n_pos, xc.shape[-1], C, ptr(xc),
+                           _st()))
+    return from_cl(xc, C)
+
+
+def avg_pool2d(x, k):
+    L = _lib.lib()
+    N, C, H, W = x.shape
+    xc = to_cl(x)
+    y = torch.zeros((N, H // k, W // k, pad4(C)), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_avgpool_nhwc(ptr(xc), N, H, W, xc.shape[-1], C, k, ptr(y), pad4(C), 0, _st()))
+    return from_cl(y, C)
+
+
+def upsample_bilinear_ac(x, size):
+    L = _lib.lib()
+    N, C, H, W = x.shape
+    xc = to_cl(x)
+    y = torch.zeros((N, size[0], size[1], pad4(C)), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_upsample_bilinear_ac_nhwc(ptr(xc), N, H, W, xc.shape[-1], C, ptr(y), size[0], size[1], pad4(C), 0, _st()))
+    return from_cl(y, C)

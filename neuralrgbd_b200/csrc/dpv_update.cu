@@ -23,26 +23,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Strided variant: thread per pixel.
 __global__ void __launch_bounds__(256)
 dpv_rows_strided_kernel(const float* __restrict__ a, const float* __restrict__ b, float sign, int n_pix, int D,
-                        long long sd, long long sp, float* __restrict__ y, long long ysd, long long ysp,
+                        long long sd, long long sp, long long bsd, long long bsp, float* __restrict__ y,
+                        long long ysd, long long ysp,
                         const float* __restrict__ dpl, float* __restrict__ depth, float* __restrict__ conf) {
   int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= n_pix) return;
   const float* pa = a + (long long)pix * sp;
-  const float* pb = b ? b + (long long)pix * sp : nullptr;
+  const float* pb = b ? b + (long long)pix * bsp : nullptr;
   float m = -INFINITY;
   for (int d = 0; d < D; ++d) {
-    float v = pa[d * sd]; if (pb) v = __fadd_rn(v, pb[d * sd]); v *= sign;
+    float v = pa[d * sd]; if (pb) v = __fadd_rn(v, pb[d * bsd]); v *= sign;
     m = fmaxf(m, v);
   }
   float s = 0.f;
   for (int d = 0; d < D; ++d) {
-    float v = pa[d * sd]; if (pb) v = __fadd_rn(v, pb[d * sd]); v *= sign;
+    float v = pa[d * sd]; if (pb) v = __fadd_rn(v, pb[d * bsd]); v *= sign;
     s += expf(v - m);
   }
   const float ls = logf(s);
   float dep = 0.f, cf = 0.f;
   for (int d = 0; d < D; ++d) {
-    float v = pa[d * sd]; if (pb) v = __fadd_rn(v, pb[d * sd]); v *= sign;
+    float v = pa[d * sd]; if (pb) v = __fadd_rn(v, pb[d * bsd]); v *= sign;
     float o = (v - m) - ls;
     if (y) y[(long long)d * ysd + (long long)pix * ysp] = o;
     if (dpl) { float p = expf(o); dep = __fadd_rn(dep, __fmul_rn(p, dpl[d])); cf = fmaxf(cf, p); }
@@ -117,20 +118,20 @@ __global__ void exp_kernel(const float* __restrict__ x, long long n, float* __re
 extern "C" {
 
 // out(d,pix) = log_softmax_d( sign * (a(d,pix) + b(d,pix)) ); b may be null.
-// a/b element (d,pix) at d*in_sd + pix*in_sp; out at d*out_sd + pix*out_sp. When d_planes is
+// a element (d,pix) at d*in_sd + pix*in_sp; b at d*b_sd + pix*b_sp; out at d*out_sd + pix*out_sp. When d_planes is
 // given also writes depth[pix] = sum_d exp(out)*d_planes[d] and conf[pix] = max_d exp(out)
 // (either may be null). out may be null when only depth/conf are wanted.
-int nrgbd_dpv_normalize(const float* a, const float* b, float sign, int n_pix, int D, long long in_sd,
-                        long long in_sp, float* out, long long out_sd, long long out_sp, const float* d_planes,
-                        float* depth, float* conf, cudaStream_t st) {
+int nrgbd_dpv_normalize(const float* a, long long in_sd, long long in_sp, const float* b, long long b_sd,
+                        long long b_sp, float sign, int n_pix, int D, float* out, long long out_sd, long long out_sp,
+                        const float* d_planes, float* depth, float* conf, cudaStream_t st) {
   NRGBD_REQUIRE(a && n_pix > 0 && D > 0, "bad arguments");
   NRGBD_REQUIRE(out || (d_planes && (depth || conf)), "nothing to compute");
-  if (in_sd == 1 && in_sp == D) {
+  if (in_sd == 1 && in_sp == D && (!b || (b_sd == 1 && b_sp == D))) {
     dpv_rows_contig_kernel<<<ceil_div((long long)n_pix * 32, 256), 256, 0, st>>>(a, b, sign, n_pix, D, out, out_sd,
                                                                                 out_sp, d_planes, depth, conf);
   } else {
-    dpv_rows_strided_kernel<<<ceil_div(n_pix, 256), 256, 0, st>>>(a, b, sign, n_pix, D, in_sd, in_sp, out, out_sd,
-                                                                  out_sp, d_planes, depth, conf);
+    dpv_rows_strided_kernel<<<ceil_div(n_pix, 256), 256, 0, st>>>(a, b, sign, n_pix, D, in_sd, in_sp, b_sd, b_sp, out,
+                                                                  out_sd, out_sp, d_planes, depth, conf);
   }
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();

@@ -1,0 +1,585 @@
+// KVNET inference engine: the native runtime behind models.KVNET.KVNET.forward.
+//
+// One engine object owns the layer plan of the reference network (models/KVNET.py:93-185,
+// models/basic.py:223-323 D-Net, :113-139 K-Net, models/psm_submodule.py:141-167 feature CNN,
+// models/Refine.py:79-107 R-Net), a stream-ordered device buffer pool, the packed conv weights and
+// the camera tables, and runs a whole depth frame as a fixed sequence of nrgbd kernels on one
+// stream: no Python between layers, no allocation after warm-up, activations channels-last.
+// Parameters are registered by their reference state_dict names (borrowed device pointers or
+// engine-owned copies of host arrays), so kvnet_*.tar checkpoints map one to one.
+#include <cmath>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/nrgbd.h"
+
+namespace {
+
+struct Act {            // channels-last activation [N][D][H][W][Cs]
+  float* p = nullptr;
+  int N = 0, D = 1, H = 0, W = 0, C = 0, Cs = 0;
+  long long pos() const { return (long long)N * D * H * W; }
+  long long floats() const { return pos() * Cs; }
+};
+
+struct Block { float* p; size_t bytes; bool busy; };
+
+struct Pool {           // stream-ordered reuse of cudaMalloc'd blocks (single stream => safe)
+  std::vector<Block> blocks;
+  size_t total = 0;
+  float* acquire(size_t bytes) {
+    int best = -1;
+    for (int i = 0; i < (int)blocks.size(); ++i)
+      if (!blocks[i].busy && blocks[i].bytes >= bytes && (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
+    if (best >= 0 && blocks[best].bytes <= bytes * 2 + (1 << 20)) { blocks[best].busy = true; return blocks[best].p; }
+    void* q = nullptr;
+    if (cudaMalloc(&q, bytes) != cudaSuccess) return nullptr;
+    blocks.push_back({(float*)q, bytes, true});
+    total += bytes;
+    return (float*)q;
+  }
+  void release(float* p) {
+    for (auto& b : blocks) if (b.p == p) { b.busy = false; return; }
+  }
+  void destroy() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); total = 0; }
+};
+
+struct ParamRef { float* p; long long n; bool owned; };
+struct Packed { float* w; int Cin, Cin_pad, Cout, Cout_pad, taps; };
+
+struct Camera {
+  bool set = false;
+  float* K = nullptr;      // 3x3
+  float* rays = nullptr;   // 3 x hw
+  float cx = 0, cy = 0, tan_hh = 0, tan_hv = 0;
+};
+
+inline int pad4(int c) { return (c + 3) / 4 * 4; }
+
+}  // namespace
+
+struct nrgbd_kvnet {
+  int H, W, D, V, F, KF;
+  int h, w;
+  float sigma;
+  int metric = 0;
+  int bn_update_running = 1;
+  std::unordered_map<std::string, ParamRef> params;
+  std::unordered_map<std::string, Packed> packed;
+  bool packed_dirty = true;
+  Camera cam[2];
+  float* d_planes = nullptr;
+  std::vector<float> d_host;
+  Pool pool;
+  double* stats = nullptr;          // [2][512]
+  float* scale = nullptr;           // [512]
+  float* shift = nullptr;           // [512]
+  float* ws_sweep = nullptr;        // V*12
+  cudaStream_t st = nullptr;
+  int rc = 0;                       // first error of the current forward
+  // persistent per-frame products (valid after forward)
+  float* bv_cur_hwd = nullptr;      // [hw][D]
+  float* dpv_hwd = nullptr;         // [hw][D]
+  float* prior_hwd = nullptr;       // [hw][D]
+  float* depth = nullptr;           // [hw] expected depth of the low-res DPV
+  float* conf = nullptr;
+  // optional per-kernel event profiling (bench.py roofline): category 0 = conv (work = flops),
+  // 1 = plane sweep (work = algorithmic bytes)
+  int profile = 0;
+  struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_free;
+};
+
+namespace {
+
+typedef nrgbd_kvnet Eng;
+
+#define ENG_CALL(e, expr)                 \
+  do {                                    \
+    if ((e)->rc == 0) {                   \
+      int _r = (expr);                    \
+      if (_r != 0) (e)->rc = _r;          \
+    }                                     \
+  } while (0)
+
+cudaEvent_t prof_event(Eng* e) {
+  if (!e->ev_free.empty()) { cudaEvent_t ev = e->ev_free.back(); e->ev_free.pop_back(); return ev; }
+  cudaEvent_t ev; cudaEventCreate(&ev); return ev;
+}
+struct ProfScope {
+  Eng* e; bool on; nrgbd_kvnet::ProfRec r;
+  ProfScope(Eng* e_, int cat, double work) : e(e_), on(e_->profile && e_->rc == 0 && e_->prof.size() < 200000) {
+    if (on) { r.a = prof_event(e); r.b = prof_event(e); r.cat = cat; r.work = work; cudaEventRecord(r.a, e->st); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, e->st); e->prof.push_back(r); } }
+};
+
+Act acquire(Eng* e, int N, int D, int H, int W, int C, int Cs = -1) {
+  Act a; a.N = N; a.D = D; a.H = H; a.W = W; a.C = C; a.Cs = Cs < 0 ? pad4(C) : Cs;
+  if (e->rc) return a;
+  a.p = e->pool.acquire((size_t)a.floats() * sizeof(float));
+  if (!a.p) { nrgbd_set_error("engine: out of device memory (%lld floats)", a.floats()); e->rc = NRGBD_ERR_NOMEM; return a; }
+  if (a.Cs != a.C) cudaMemsetAsync(a.p, 0, (size_t)a.floats() * sizeof(float), e->st);   // pad channels must be 0
+  return a;
+}
+void release(Eng* e, Act& a) { if (a.p) e->pool.release(a.p); a.p = nullptr; }
+
+float* param(Eng* e, const std::string& name) {
+  auto it = e->params.find(name);
+  if (it == e->params.end()) {
+    if (e->rc == 0) { nrgbd_set_error("engine: parameter '%s' was never set", name.c_str()); e->rc = NRGBD_ERR_BAD_ARG; }
+    return nullptr;
+  }
+  return it->second.p;
+}
+float* param_opt(Eng* e, const std::string& name) {
+  auto it = e->params.find(name);
+  return it == e->params.end() ? nullptr : it->second.p;
+}
+
+const Packed* packw(Eng* e, const std::string& name, int Cout, int Cin, int taps, bool transposed) {
+  auto it = e->packed.find(name);
+  if (it != e->packed.end()) return &it->second;
+  float* src = param(e, name);
+  if (!src) return nullptr;
+  auto pr = e->params[name];
+  if (pr.n != (long long)Cout * Cin * taps) {
+    if (e->rc == 0) { nrgbd_set_error("engine: parameter '%s' has %lld elements, expected %lld", name.c_str(), pr.n, (long long)Cout * Cin * taps); e->rc = NRGBD_ERR_BAD_ARG; }
+    return nullptr;
+  }
+  Packed pk; pk.Cin = Cin; pk.Cout = Cout; pk.taps = taps; pk.Cin_pad = pad4(Cin); pk.Cout_pad = pad4(Cout);
+  size_t bytes = (size_t)taps * pk.Cin_pad * pk.Cout_pad * sizeof(float);
+  void* q = nullptr;
+  if (cudaMalloc(&q, bytes) != cudaSuccess) { e->rc = NRGBD_ERR_NOMEM; nrgbd_set_error("engine: cudaMalloc failed for packed weight"); return nullptr; }
+  pk.w = (float*)q;
+  ENG_CALL(e, nrgbd_pack_conv_weight(src, transposed ? 1 : 0, Cout, Cin, taps, pk.Cin_pad, pk.Cout_pad, pk.w, (nrgbd_stream_t)e->st));
+  e->packed[name] = pk;
+  return &e->packed[name];
+}
+
+// conv (2-D when x.D == 1 and kd == 1) into a fresh activation or into `dst` at channel c_off
+Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k, int stride, int pad, int dil,
+         const char* bias_name, bool leaky, bool want_stats, Act* dst = nullptr, int c_off = 0, int out_Cs = -1) {
+  int Ho = (x.H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  int Wo = (x.W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  Act y;
+  if (dst) y = *dst; else y = acquire(e, x.N, x.D, Ho, Wo, Cout, out_Cs);
+  const Packed* pk = packw(e, wname, Cout, x.C, kd * k * k, false);
+  float* b = bias_name ? param(e, bias_name) : nullptr;
+  if (e->rc) return y;
+  if (want_stats) cudaMemsetAsync(e->stats, 0, sizeof(double) * 2 * Cout, e->st);
+  ProfScope ps(e, 0, 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k);
+  ENG_CALL(e, nrgbd_conv_nhwc(x.p, x.N, x.D, x.H, x.W, pk->Cin_pad, x.Cs, pk->w, b, Cout, pk->Cout_pad, kd, k, k, stride,
+                              pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
+                              (nrgbd_stream_t)e->st));
+  return y;
+}
+
+// Conv (no bias) + BatchNorm(batch statistics) [+ ReLU] [+ residual]; BN applied in place.
+// `pre` is the Sequential(Conv, BN) prefix: weights pre.0.weight, pre.1.{weight,bias,running_*}.
+Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k, int stride, int pad, int dil,
+           bool relu, const Act* res) {
+  int p = (kd == 1 && dil > 1) ? dil : pad;          // psm_submodule.convbn :13
+  Act y = conv(e, x, pre + ".0.weight", Cout, kd, k, stride, p, dil, nullptr, false, true);
+  float* g = param(e, pre + ".1.weight");
+  float* b = param(e, pre + ".1.bias");
+  float* rm = e->bn_update_running ? param_opt(e, pre + ".1.running_mean") : nullptr;
+  float* rv = e->bn_update_running ? param_opt(e, pre + ".1.running_var") : nullptr;
+  if (e->rc) return y;
+  ENG_CALL(e, nrgbd_bn_finalize(e->stats, Cout, (double)y.pos(), g, b, 1e-5f, e->scale, e->shift, rm && rv ? rm : nullptr,
+                                rm && rv ? rv : nullptr, 0.1f, (nrgbd_stream_t)e->st));
+  ENG_CALL(e, nrgbd_bn_apply(y.p, e->scale, e->shift, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, y.p,
+                             (nrgbd_stream_t)e->st));
+  return y;
+}
+
+// psm_submodule.BasicBlock :31-49
+Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, int dil, bool down) {
+  Act t = convbn(e, x, pre + ".conv1.0", planes, 1, 3, stride, 1, dil, true, nullptr);
+  Act sc; const Act* res = &x;
+  if (down) {
+    // downsample = Sequential(Conv2d 1x1 stride, BatchNorm2d) :125-131 -> names downsample.0 / downsample.1
+    sc = conv(e, x, pre + ".downsample.0.weight", planes, 1, 1, stride, 0, 1, nullptr, false, true);
+    float* g = param(e, pre + ".downsample.1.weight"); float* b = param(e, pre + ".downsample.1.bias");
+    float* rm = e->bn_update_running ? param_opt(e, pre + ".downsample.1.running_mean") : nullptr;
+    float* rv = e->bn_update_running ? param_opt(e, pre + ".downsample.1.running_var") : nullptr;
+    if (!e->rc) {
+      ENG_CALL(e, nrgbd_bn_finalize(e->stats, planes, (double)sc.pos(), g, b, 1e-5f, e->scale, e->shift,
+                                    rm && rv ? rm : nullptr, rm && rv ? rv : nullptr, 0.1f, (nrgbd_stream_t)e->st));
+      ENG_CALL(e, nrgbd_bn_apply(sc.p, e->scale, e->shift, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, (nrgbd_stream_t)e->st));
+    }
+    res = &sc;
+  }
+  Act o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res);
+  release(e, t);
+  if (down) release(e, sc);
+  return o;
+}
+
+Act make_layer(Eng* e, Act x, bool own_x, const std::string& pre, int planes, int blocks, int stride, int dil, bool down) {
+  Act cur = x;
+  for (int i = 0; i < blocks; ++i) {
+    Act o = basic_block(e, cur, pre + "." + std::to_string(i), planes, i == 0 ? stride : 1, dil, down && i == 0);
+    if (i > 0 || own_x) release(e, cur);
+    cur = o;
+  }
+  return cur;
+}
+
+// psm_submodule.feature_extraction.forward :141-167 -> (layer1 output @1/2, features @1/4)
+void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
+  const std::string P = "feature_extractor.feature_extraction";
+  Act a = convbn(e, x0, P + ".firstconv.0", 32, 1, 3, 2, 1, 1, true, nullptr);
+  Act b = convbn(e, a, P + ".firstconv.2", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, a);
+  Act c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, b);
+  Act l1 = make_layer(e, c, true, P + ".layer1", 32, 3, 1, 1, false);
+  Act raw = make_layer(e, l1, false, P + ".layer2", 64, 16, 2, 1, true);
+  Act l3 = make_layer(e, raw, false, P + ".layer3", 128, 3, 1, 1, true);
+  Act skip = make_layer(e, l3, true, P + ".layer4", 128, 3, 1, 2, false);
+  Act cat = acquire(e, skip.N, 1, skip.H, skip.W, 320);
+  if (!e->rc) {
+    ENG_CALL(e, nrgbd_copy_channels(raw.p, raw.pos(), raw.Cs, 0, 64, 0, cat.p, cat.Cs, 0, (nrgbd_stream_t)e->st));
+    ENG_CALL(e, nrgbd_copy_channels(skip.p, skip.pos(), skip.Cs, 0, 128, 0, cat.p, cat.Cs, 64, (nrgbd_stream_t)e->st));
+  }
+  // cat order (:161): raw, skip, branch4, branch3, branch2, branch1
+  const int ks[4] = {64, 32, 16, 8};
+  const int offs[4] = {288, 256, 224, 192};
+  for (int bi = 0; bi < 4 && !e->rc; ++bi) {
+    int k = ks[bi];
+    if (skip.H / k < 1 || skip.W / k < 1) {
+      nrgbd_set_error("engine: frame too small for the SPP AvgPool2d(%d) branch (need H/4, W/4 >= 64)", k);
+      e->rc = NRGBD_ERR_BAD_ARG; break;
+    }
+    Act pl = acquire(e, skip.N, 1, skip.H / k, skip.W / k, 128);
+    ENG_CALL(e, nrgbd_avgpool_nhwc(skip.p, skip.N, skip.H, skip.W, skip.Cs, 128, k, pl.p, pl.Cs, 0, (nrgbd_stream_t)e->st));
+    Act br = convbn(e, pl, P + ".branch" + std::to_string(bi + 1) + ".1", 32, 1, 1, 1, 0, 1, true, nullptr);
+    ENG_CALL(e, nrgbd_upsample_bilinear_ac_nhwc(br.p, br.N, br.H, br.W, br.Cs, 32, cat.p, cat.H, cat.W, cat.Cs, offs[bi],
+                                                (nrgbd_stream_t)e->st));
+    release(e, pl); release(e, br);
+  }
+  release(e, raw); release(e, skip);
+  Act lc = convbn(e, cat, P + ".lastconv.0", 128, 1, 3, 1, 1, 1, true, nullptr);
+  release(e, cat);
+  feat_out = conv(e, lc, P + ".lastconv.2.weight", e->F, 1, 1, 1, 0, 1, nullptr, false, false);
+  release(e, lc);
+  l1_out = l1;
+}
+
+// models/Refine.py:79-107. prob source: log-DPV pixel-major [hw][D]; returns log-DPV [H*W][D].
+Act r_net(Eng* e, const float* bv_hwd, const float* feat_ref, const float* l1_ref, const Act& frame_ref) {
+  const int D = e->D, h = e->h, w = e->w, H = e->H, W = e->W, F = e->F;
+  const long long hw = (long long)h * w;
+  nrgbd_stream_t st = (nrgbd_stream_t)e->st;
+  Act in0 = acquire(e, 1, 1, h, w, D + F);
+  if (!e->rc) {
+    ENG_CALL(e, nrgbd_copy_channels(bv_hwd, hw, D, 0, D, 1, in0.p, in0.Cs, 0, st));           // torch.exp(BV)
+    ENG_CALL(e, nrgbd_copy_channels(feat_ref, hw, pad4(F), 0, F, 0, in0.p, in0.Cs, D, st));
+  }
+  Act a = conv(e, in0, "r_net.conv0.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0.0.bias", true, false); release(e, in0);
+  Act b = conv(e, a, "r_net.conv0_1.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0_1.0.bias", true, false); release(e, a);
+  Act t0 = acquire(e, 1, 1, 2 * h, 2 * w, D + F / 2);
+  const Packed* pk = packw(e, "r_net.trans_conv0.0.weight", D, D + F, 16, true);
+  float* tb = param(e, "r_net.trans_conv0.0.bias");
+  if (!e->rc) {
+    ProfScope ps(e, 0, 2.0 * 4.0 * hw * D * (D + F) * 4);
+    ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc(b.p, 1, h, w, pk->Cin_pad, b.Cs, pk->w, tb, D, pk->Cout_pad, t0.p, t0.Cs, 0, 1, st));
+    ENG_CALL(e, nrgbd_copy_channels(l1_ref, 4 * hw, pad4(F / 2), 0, F / 2, 0, t0.p, t0.Cs, D, st));
+  }
+  release(e, b);
+  Act c = conv(e, t0, "r_net.conv1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1.0.bias", true, false); release(e, t0);
+  Act d = conv(e, c, "r_net.conv1_1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1_1.0.bias", true, false); release(e, c);
+  Act t1 = acquire(e, 1, 1, H, W, D + 3);
+  pk = packw(e, "r_net.trans_conv1.0.weight", D, D + F / 2, 16, true);
+  tb = param(e, "r_net.trans_conv1.0.bias");
+  if (!e->rc) {
+    ProfScope ps(e, 0, 2.0 * 16.0 * hw * D * (D + F / 2) * 4);
+    ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc(d.p, 1, 2 * h, 2 * w, pk->Cin_pad, d.Cs, pk->w, tb, D, pk->Cout_pad, t1.p, t1.Cs, 0, 1, st));
+    ENG_CALL(e, nrgbd_copy_channels(frame_ref.p, (long long)H * W, frame_ref.Cs, 0, 3, 0, t1.p, t1.Cs, D, st));
+  }
+  release(e, d);
+  Act f = conv(e, t1, "r_net.conv2.0.weight", D + 3, 1, 3, 1, 1, 1, "r_net.conv2.0.bias", true, false); release(e, t1);
+  Act g = conv(e, f, "r_net.conv2_1.0.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_1.0.bias", true, false); release(e, f);
+  Act o = conv(e, g, "r_net.conv2_2.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_2.bias", false, false, nullptr, 0, D); release(e, g);
+  // F.log_softmax(conv2_2_out, dim=1): channels are contiguous per pixel (Cs == D)
+  if (!e->rc)
+    ENG_CALL(e, nrgbd_dpv_normalize(o.p, 1, D, nullptr, 0, 0, 1.f, H * W, D, o.p, 1, D, nullptr, nullptr, nullptr, st));
+  return o;
+}
+
+// models/basic.py:113-139 on a channels-last volume [D][h][w][CK] -> gain [D][hw] (DHW, Cs = 1)
+Act kv_net(Eng* e, const Act& vol) {
+  const int f = e->KF;
+  auto cb = [&](const Act& x, const std::string& name, bool relu, const Act* res) {
+    return convbn(e, x, name, f, 3, 3, 1, 1, 1, relu, res);
+  };
+  Act a = cb(vol, "kv_net.dres0.0", true, nullptr);
+  Act c = cb(a, "kv_net.dres0.2", true, nullptr); release(e, a);
+  for (int i = 1; i <= 4; ++i) {
+    std::string p = "kv_net.dres" + std::to_string(i);
+    Act r = cb(c, p + ".0", true, nullptr);
+    Act o = cb(r, p + ".2", false, &c);
+    release(e, r); release(e, c);
+    c = o;
+  }
+  Act o = cb(c, "kv_net.classify.0", true, nullptr); release(e, c);
+  Act gain = conv(e, o, "kv_net.classify.2.weight", 1, 3, 3, 1, 1, 1, nullptr, false, false, nullptr, 0, 1);
+  release(e, o);
+  return gain;
+}
+
+int upload(float** dst, const float* host, size_t n) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (cudaMalloc((void**)dst, n * sizeof(float)) != cudaSuccess) return NRGBD_ERR_NOMEM;
+  if (cudaMemcpy(*dst, host, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return NRGBD_ERR_CUDA;
+  return NRGBD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nrgbd_kvnet_create(int H, int W, int D, int V, int feature_dim, int kv_feature_dim, float sigma, int metric,
+                       nrgbd_kvnet** out) {
+  NRGBD_REQUIRE(out, "null handle pointer");
+  NRGBD_REQUIRE(H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "H and W must be positive multiples of 4");
+  NRGBD_REQUIRE(H / 4 >= 64 && W / 4 >= 64, "H/4 and W/4 must be >= 64 (SPP AvgPool2d(64), psm_submodule.py:103)");
+  NRGBD_REQUIRE(D > 0 && V > 0 && feature_dim > 0 && feature_dim % 8 == 0 && kv_feature_dim > 0 && kv_feature_dim % 4 == 0,
+                "bad network dimensions");
+  NRGBD_REQUIRE(metric == 0 || metric == 1, "undefined metric for feature distance ...");
+  nrgbd_kvnet* e = new nrgbd_kvnet();
+  e->H = H; e->W = W; e->D = D; e->V = V; e->F = feature_dim; e->KF = kv_feature_dim;
+  e->h = H / 4; e->w = W / 4; e->sigma = sigma; e->metric = metric;
+  const size_t hw = (size_t)e->h * e->w;
+  bool ok = cudaMalloc((void**)&e->stats, sizeof(double) * 2 * 512) == cudaSuccess &&
+            cudaMalloc((void**)&e->scale, sizeof(float) * 512) == cudaSuccess &&
+            cudaMalloc((void**)&e->shift, sizeof(float) * 512) == cudaSuccess &&
+            cudaMalloc((void**)&e->ws_sweep, sizeof(float) * 12 * V) == cudaSuccess &&
+            cudaMalloc((void**)&e->bv_cur_hwd, sizeof(float) * hw * D) == cudaSuccess &&
+            cudaMalloc((void**)&e->dpv_hwd, sizeof(float) * hw * D) == cudaSuccess &&
+            cudaMalloc((void**)&e->prior_hwd, sizeof(float) * hw * D) == cudaSuccess &&
+            cudaMalloc((void**)&e->depth, sizeof(float) * hw) == cudaSuccess &&
+            cudaMalloc((void**)&e->conf, sizeof(float) * hw) == cudaSuccess;
+  if (!ok) { nrgbd_set_error("nrgbd_kvnet_create: cudaMalloc failed"); delete e; return NRGBD_ERR_NOMEM; }
+  *out = e;
+  return NRGBD_OK;
+}
+
+int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
+  if (!e) return NRGBD_OK;
+  for (auto& kv : e->params) if (kv.second.owned) cudaFree(kv.second.p);
+  for (auto& kv : e->packed) cudaFree(kv.second.w);
+  for (int i = 0; i < 2; ++i) { cudaFree(e->cam[i].K); cudaFree(e->cam[i].rays); }
+  cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
+  cudaFree(e->bv_cur_hwd); cudaFree(e->dpv_hwd); cudaFree(e->prior_hwd); cudaFree(e->depth); cudaFree(e->conf);
+  e->pool.destroy();
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto ev : e->ev_free) cudaEventDestroy(ev);
+  delete e;
+  return NRGBD_OK;
+}
+
+// Register a parameter under its reference state_dict name. is_device != 0: `data` is a device
+// pointer the engine borrows (must outlive the engine or be re-set); else a host array that is copied.
+// Setting a conv weight again invalidates its packed copy.
+int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, long long n, int is_device) {
+  NRGBD_REQUIRE(e && name && data && n > 0, "bad arguments");
+  std::string key(name);
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);                         // DataParallel prefix
+  const std::string alias = "d_net.feature_extraction.";                          // same tensors, second name (KVNET.py:63-67)
+  if (key.rfind(alias, 0) == 0) key = "feature_extractor." + key.substr(alias.size());
+  auto it = e->params.find(key);
+  if (it != e->params.end()) {
+    if (it->second.owned) cudaFree(it->second.p);
+    e->params.erase(it);
+  }
+  auto pk = e->packed.find(key);
+  if (pk != e->packed.end()) { cudaFree(pk->second.w); e->packed.erase(pk); }
+  ParamRef r; r.n = n; r.owned = !is_device;
+  if (is_device) {
+    r.p = const_cast<float*>(data);
+  } else {
+    void* q = nullptr;
+    NRGBD_CUDA_CHECK(cudaMalloc(&q, n * sizeof(float)));
+    NRGBD_CUDA_CHECK(cudaMemcpy(q, data, n * sizeof(float), cudaMemcpyHostToDevice));
+    r.p = (float*)q;
+  }
+  e->params[key] = r;
+  return NRGBD_OK;
+}
+
+// slot 0: the intrinsics captured at construction (D-Net sweep, KVNET.py:64-67 / basic.py:270-278)
+// slot 1: the per-call intrinsics (K-Net image warp KVNET.py:160-161 and DPV propagation)
+// K_host 3x3 (intrinsic_M_cuda), rays_host 3 x (h*w) (unit_ray_array_2D), cx/cy from intrinsic_M,
+// hfov/vfov in degrees.
+int nrgbd_kvnet_set_camera(nrgbd_kvnet* e, int slot, const float* K_host, const float* rays_host, float cx, float cy,
+                           double hfov_deg, double vfov_deg) {
+  NRGBD_REQUIRE(e && (slot == 0 || slot == 1) && K_host && rays_host, "bad arguments");
+  Camera& c = e->cam[slot];
+  int rc = upload(&c.K, K_host, 9);
+  if (rc == NRGBD_OK) rc = upload(&c.rays, rays_host, (size_t)3 * e->h * e->w);
+  if (rc != NRGBD_OK) { nrgbd_set_error("nrgbd_kvnet_set_camera: upload failed"); return rc; }
+  c.cx = cx; c.cy = cy;
+  c.tan_hh = (float)std::tan(hfov_deg * M_PI / 180.0 * .5);
+  c.tan_hv = (float)std::tan(vfov_deg * M_PI / 180.0 * .5);
+  c.set = true;
+  return NRGBD_OK;
+}
+
+int nrgbd_kvnet_set_planes(nrgbd_kvnet* e, const float* d_host, int D) {
+  NRGBD_REQUIRE(e && d_host && D == e->D, "d_candi length must equal the engine's D");
+  e->d_host.assign(d_host, d_host + D);
+  int rc = upload(&e->d_planes, d_host, D);
+  if (rc != NRGBD_OK) nrgbd_set_error("nrgbd_kvnet_set_planes: upload failed");
+  return rc;
+}
+
+int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value) {
+  NRGBD_REQUIRE(e && key, "bad arguments");
+  std::string k(key);
+  if (k == "bn_update_running") { e->bn_update_running = value; return NRGBD_OK; }
+  if (k == "profile") { e->profile = value; return NRGBD_OK; }
+  nrgbd_set_error("nrgbd_kvnet_set_option: unknown option '%s'", key);
+  return NRGBD_ERR_BAD_ARG;
+}
+
+long long nrgbd_kvnet_workspace_bytes(nrgbd_kvnet* e) { return e ? (long long)e->pool.total : 0; }
+
+// Sum of the event-timed durations (ms), work units and launch count of one profiled kernel
+// category since the last read (category 0: conv kernels, work = algorithmic flops; 1: plane sweep,
+// work = algorithmic bytes). Synchronises on the recorded events and clears the records.
+int nrgbd_kvnet_profile_read(nrgbd_kvnet* e, int category, double* ms, double* work, long long* launches) {
+  NRGBD_REQUIRE(e && ms && work && launches, "bad arguments");
+  *ms = 0; *work = 0; *launches = 0;
+  std::vector<nrgbd_kvnet::ProfRec> keep;
+  for (auto& r : e->prof) {
+    if (r.cat != category) { keep.push_back(r); continue; }
+    float t = 0.f;
+    NRGBD_CUDA_CHECK(cudaEventSynchronize(r.b));
+    NRGBD_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    *ms += t; *work += r.work; *launches += 1;
+    e->ev_free.push_back(r.a); e->ev_free.push_back(r.b);
+  }
+  e->prof.swap(keep);
+  return NRGBD_OK;
+}
+
+// One depth frame (models/KVNET.py:93-185, if_refined=True, refineNet_name='DPV').
+//  frames  [V+1][3][H][W]  source views then the reference frame (basic.py:245 cat order), device
+//  poses   [V][4][4]       relative poses E_src.E_ref^-1, device
+//  bv_predict [D][h][w] or NULL: NULL -> first-window branch (:138-140). (The NaN-sentinel test of
+//  :142 reads one element on the host and is done by the caller.)
+//  outputs (device, any may be NULL): dmap_cur_refined [D][H][W], dmap_refined [D][H][W],
+//  bv_cur [D][h][w], dpv [D][h][w]; depth_lowres/conf_lowres [h][w] = expected depth / max prob of dpv.
+int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses, const float* bv_predict,
+                        float* dmap_cur_refined, float* dmap_refined, float* bv_cur, float* dpv, float* depth_lowres,
+                        float* conf_lowres, nrgbd_stream_t stream) {
+  NRGBD_REQUIRE(e && frames && poses, "null input");
+  NRGBD_REQUIRE(e->cam[0].set && e->d_planes, "camera / depth planes not set");
+  NRGBD_REQUIRE(!bv_predict || e->cam[1].set, "per-call camera (slot 1) not set");
+  e->st = (cudaStream_t)stream; e->rc = 0;
+  nrgbd_stream_t st = stream;
+  const int H = e->H, W = e->W, D = e->D, V = e->V, h = e->h, w = e->w, F = e->F, N = V + 1;
+  const long long hw = (long long)h * w, HW = (long long)H * W;
+
+  // ---- D-Net: features for the V+1 frames as one batch (basic.py:244-252) ------------------------
+  Act x0 = acquire(e, N, 1, H, W, 3);
+  ENG_CALL(e, nrgbd_nchw_to_nhwc(frames, N, 3, HW, x0.p, x0.Cs, 0, st));
+  Act l1, feat;
+  feature_cnn(e, x0, l1, feat);
+  // image intensity features: avg_pool2d(rgb, 4) (basic.py:254-263) -> the sweep's narrow layout [N][hw][4]
+  Act rgbq = acquire(e, N, 1, h, w, 3);
+  ENG_CALL(e, nrgbd_avgpool_nhwc(x0.p, N, H, W, x0.Cs, 3, 4, rgbq.p, rgbq.Cs, 0, st));
+  // Rs / ts (basic.py:266-267): gather 3x3 and 3 from the 4x4 poses
+  float* Rt = e->pool.acquire(sizeof(float) * 12 * V);
+  if (!Rt && !e->rc) { e->rc = NRGBD_ERR_NOMEM; nrgbd_set_error("engine: out of memory"); }
+  if (!e->rc) {
+    for (int v = 0; v < V; ++v) {
+      cudaMemcpy2DAsync(Rt + v * 9, 3 * sizeof(float), poses + v * 16, 4 * sizeof(float), 3 * sizeof(float), 3,
+                        cudaMemcpyDeviceToDevice, e->st);
+      cudaMemcpy2DAsync(Rt + 9 * V + v * 3, sizeof(float), poses + v * 16 + 3, 4 * sizeof(float), sizeof(float), 3,
+                        cudaMemcpyDeviceToDevice, e->st);
+    }
+  }
+  const float* Rs = Rt; const float* ts = Rt ? Rt + 9 * V : nullptr;
+  const size_t featS = (size_t)hw * pad4(F);
+  const Camera& c0 = e->cam[0];
+  if (!e->rc) {
+    {
+    ProfScope ps(e, 1, ((1.0 + V) * (F + 3) + D + 3) * (double)hw * 4.0);
+    ENG_CALL(e, nrgbd_plane_sweep_cost_packed(feat.p + (size_t)V * featS, rgbq.p + (size_t)V * hw * 4, feat.p, rgbq.p, F, 3, V, D,
+                                              h, w, c0.K, Rs, ts, c0.rays, e->d_planes, c0.cx, c0.cy, e->sigma, e->metric,
+                                              e->ws_sweep, e->dpv_hwd /* scratch: cost */, st));
+    }
+    // BV = log_softmax(-costV) (basic.py:299-300)
+    ENG_CALL(e, nrgbd_dpv_normalize(e->dpv_hwd, 1, D, nullptr, 0, 0, -1.f, (int)hw, D, e->bv_cur_hwd, 1, D, e->d_planes,
+                                    e->depth, e->conf, st));
+  }
+  if (bv_cur) ENG_CALL(e, nrgbd_transpose2d(e->bv_cur_hwd, (int)hw, D, bv_cur, st));
+
+  // ---- R-Net on the measurement (KVNET.py:134) ----------------------------------------------------
+  const float* feat_ref = feat.p + (size_t)V * featS;
+  const float* l1_ref = l1.p ? l1.p + (size_t)V * 4 * hw * l1.Cs : nullptr;
+  Act frame_ref = x0; frame_ref.N = 1; frame_ref.p = x0.p ? x0.p + (size_t)V * HW * x0.Cs : nullptr;
+  const bool steady = bv_predict != nullptr;
+  if (dmap_cur_refined || (!steady && dmap_refined)) {
+    Act r = r_net(e, e->bv_cur_hwd, feat_ref, l1_ref, frame_ref);
+    if (dmap_cur_refined) ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_cur_refined, st));
+    if (!steady && dmap_refined) ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_refined, st));
+    release(e, r);
+  }
+  if (!steady) {
+    // first window: DPV = BV_cur (KVNET.py:138-140)
+    if (!e->rc) cudaMemcpyAsync(e->dpv_hwd, e->bv_cur_hwd, sizeof(float) * hw * D, cudaMemcpyDeviceToDevice, e->st);
+    if (dpv) ENG_CALL(e, nrgbd_transpose2d(e->bv_cur_hwd, (int)hw, D, dpv, st));
+  } else {
+    // ---- K-Net (KVNET.py:147-173) ------------------------------------------------------------------
+    const Camera& c1 = e->cam[1];
+    const int CK = 3 * V + 4;
+    ENG_CALL(e, nrgbd_transpose2d(bv_predict, D, (int)hw, e->prior_hwd, st));
+    Act vol = acquire(e, 1, D, h, w, CK, pad4(CK));
+    ENG_CALL(e, nrgbd_knet_input_volume(rgbq.p, rgbq.p + (size_t)V * hw * 4, e->bv_cur_hwd, e->prior_hwd, V, D, h, w, vol.Cs,
+                                        c1.K, Rs, ts, c1.rays, e->d_planes, c1.cx, c1.cy, e->ws_sweep, vol.p, st));
+    Act gain = kv_net(e, vol);
+    release(e, vol);
+    // DPV = log_softmax(gain + BV_predict) (:172-173); gain is [D][hw], prior pixel-major
+    ENG_CALL(e, nrgbd_dpv_normalize(gain.p, hw, 1, e->prior_hwd, 1, D, 1.f, (int)hw, D, e->dpv_hwd, 1, D, e->d_planes, e->depth,
+                                    e->conf, st));
+    release(e, gain);
+    if (dpv) ENG_CALL(e, nrgbd_transpose2d(e->dpv_hwd, (int)hw, D, dpv, st));
+    if (dmap_refined) {
+      Act r = r_net(e, e->dpv_hwd, feat_ref, l1_ref, frame_ref);
+      ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_refined, st));
+      release(e, r);
+    }
+  }
+  if (depth_lowres && !e->rc) cudaMemcpyAsync(depth_lowres, e->depth, sizeof(float) * hw, cudaMemcpyDeviceToDevice, e->st);
+  if (conf_lowres && !e->rc) cudaMemcpyAsync(conf_lowres, e->conf, sizeof(float) * hw, cudaMemcpyDeviceToDevice, e->st);
+  release(e, x0); release(e, l1); release(e, feat); release(e, rgbq);
+  if (Rt) e->pool.release(Rt);
+  if (e->rc == 0) { cudaError_t ce = cudaGetLastError(); if (ce != cudaSuccess) { nrgbd_set_error("nrgbd_kvnet_forward: %s", cudaGetErrorString(ce)); e->rc = NRGBD_ERR_CUDA; } }
+  return e->rc;
+}
+
+// Propagate the engine's current DPV into the next camera (test_utils/test_KVNet.py:46-59):
+// BV_predict' = clamp(resample(dpv, rel_pose_inv, pad=log(1/D)), -1000, 0), written to out [D][h][w].
+int nrgbd_kvnet_propagate(nrgbd_kvnet* e, const float* dpv_dhw, const float* rel_pose_inv_dev, float* out_dhw,
+                          nrgbd_stream_t stream) {
+  NRGBD_REQUIRE(e && rel_pose_inv_dev && out_dhw, "null pointer");
+  NRGBD_REQUIRE(e->cam[1].set && e->d_planes && !e->d_host.empty(), "per-call camera / planes not set");
+  const int D = e->D, h = e->h, w = e->w;
+  float zmax = e->d_host[0], zmin = e->d_host[0];
+  for (float d : e->d_host) { zmax = fmaxf(zmax, d); zmin = fminf(zmin, d); }
+  const float z_half = (zmax + zmin) * .5f, z_radius = (zmax - zmin) * .5f;
+  const Camera& c = e->cam[1];
+  const float pad = (float)std::log(1.0 / (double)D);
+  if (dpv_dhw)
+    return nrgbd_resample_dpv(dpv_dhw, (long long)h * w, 1, rel_pose_inv_dev, c.rays, e->d_planes, D, h, w, c.tan_hh, c.tan_hv,
+                              z_half, z_radius, pad, 1, -1000.f, 0.f, out_dhw, (long long)h * w, 1, stream);
+  return nrgbd_resample_dpv(e->dpv_hwd, 1, D, rel_pose_inv_dev, c.rays, e->d_planes, D, h, w, c.tan_hh, c.tan_hv, z_half,
+                            z_radius, pad, 1, -1000.f, 0.f, out_dhw, (long long)h * w, 1, stream);
+}
+
+}  // extern "C"

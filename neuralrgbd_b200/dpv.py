@@ -29,6 +29,6 @@ def log_softmax_planes(x, sign=1.0, add=None, d_candi=None):
             dpl = torch.from_numpy(np.asarray(d_candi).astype(np.float32)).to(a.device)
             depth = torch.empty((1, H, W), device=a.device, dtype=torch.float32)
             conf = torch.empty((1, H, W), device=a.device, dtype=torch.float32)
-        check(L.nrgbd_dpv_normalize(ptr(a), ptr(b), _F(sign), H * W, D, H * W, 1, ptr(out), H * W, 1, ptr(dpl),
+        check(L.nrgbd_dpv_normalize(ptr(a), H * W, 1, ptr(b), H * W, 1, _F(sign), H * W, D, ptr(out), H * W, 1, ptr(dpl),
                                     ptr(depth), ptr(conf), _stream()))
     return out if d_candi is None else (out, depth, conf)

@@ -113,3 +113,16 @@ def test_pinning_record_within_bounds():
         elif k.startswith('kvnet/') and isinstance(v, dict):
             assert v['BV_cur_prob'] <= 1e-4 and v['dmap_cur_refined_prob'] <= 1e-4
             assert v['DPV_prob'] <= 5e-4 and v['depth_mm'] <= 1.0
+
+
+def test_torch_port_reproduces_reference(golden):
+    """oracle/torch_port.py (the timed CPU arm of bench.py) uses the same ATen ops as the
+    reference: its first-window outputs must equal the recorded reference outputs exactly."""
+    from oracle import torch_port as TP
+    name = 'kvnet_256x320_d8'
+    c = cases.kvnet_case(name)
+    cam = cases.cam_for(O.make_cam_intrinsics, c['W'] // 4, c['H'] // 4)
+    ref_f, src_f, poses = cases.window(c, 2)
+    r, bv, dep = TP.kvnet_first_window(c['sd'], ref_f, src_f, poses, cam, c['d'], c['sigma'])
+    assert maxabs(cases.subsample(bv), golden['kvnet/%s/step0/BV_cur' % name]) <= 1e-6
+    assert maxabs(cases.subsample(r), golden['kvnet/%s/step0/dmap_cur_refined' % name]) <= 1e-6

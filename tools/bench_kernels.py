@@ -67,7 +67,7 @@ def main():
     dep = torch.empty(hw, device=dev); conf = torch.empty(hw, device=dev)
 
     def norm():
-        check(L.nrgbd_dpv_normalize(ptr(cost), None, F(-1.), hw, D, 1, D, ptr(out), 1, D, ptr(dpl), ptr(dep), ptr(conf), st()))
+        check(L.nrgbd_dpv_normalize(ptr(cost), 1, D, None, 0, 0, F(-1.), hw, D, ptr(out), 1, D, ptr(dpl), ptr(dep), ptr(conf), st()))
     med, mn = timeit(norm)
     res['dpv_normalize_hwd'] = dict(us_med=med, us_min=mn, GBps=2 * hw * D * 4 / med / 1e3)
     E = torch.from_numpy(np.linalg.inv(poses[V // 2].astype(np.float64)).astype(np.float32)).to(dev)
