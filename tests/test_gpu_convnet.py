@@ -152,11 +152,13 @@ def test_kvnet_forward_streaming_vs_reference(golden, name):
             assert np.isfinite(a).all()
         if bv_pred is None:
             assert full[0] is full[1] and full[2] is full[3]          # KVNET.py:138-140 returns the same tensors
-        # expected depth within 1 mm of the reference's (from the golden DPV, sub-sampled grid)
-        from neuralrgbd_b200.mutils import misc
-        dep = misc.depth_val_regression(full[3], c['d']).cpu().numpy()
+        # expected depth within 1 mm of the reference's (both from the sub-sampled DPV grid)
+        dep = O.depth_val_regression(cases.subsample(full[3].cpu().numpy()), c['d'])
         dep_ref = O.depth_val_regression(golden[key + '/DPV'], c['d'])
-        assert maxabs(cases.subsample(dep), dep_ref) * 1000.0 <= 1.0
+        assert maxabs(dep, dep_ref) * 1000.0 <= 1.0
+        from neuralrgbd_b200.mutils import misc
+        dep_dev = misc.depth_val_regression(full[3], c['d']).cpu().numpy()
+        assert maxabs(dep_dev, O.depth_val_regression(full[3].cpu().numpy(), c['d'])) * 1000.0 <= 0.01
         # the reference's inference step: forward + propagation
         Ref_Dats = [{'img': T(ref_f)}]
         Src_Dats = [[{'img': T(src_f[0, v:v + 1])} for v in range(src_f.shape[1])]]
