@@ -156,7 +156,7 @@ def run_reference(args):
 def run_engine(args):
     import torch
     import torch.distributed as dist
-    from neuralrgbd_b200 import _lib, arch, camera, synth
+    from neuralrgbd_b200 import _lib, arch, camera, sharding, synth
     from neuralrgbd_b200._lib import ptr, check
     from neuralrgbd_b200.models.KVNET import KVNET
     from neuralrgbd_b200.mutils import misc
@@ -182,9 +182,7 @@ def run_engine(args):
         sd = arch.synth_state_dict(5, 64, D_PLANES, 2, 64)
         model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     model = model.to(dev)
-    if world > 1:
-        for t in list(model.parameters()) + [b for b in model.buffers() if b.dtype == torch.float32]:
-            dist.broadcast(t.data, src=0)
+    sharding.broadcast_module(model, src=0)
 
     n_win = 4
     wins = make_windows(n_win, seed=7 + rank)           # every rank owns its own windows (frames shard naturally)

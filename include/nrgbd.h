@@ -136,6 +136,23 @@ int nrgbd_bn_finalize(const double* stats, int C, double count, const float* gam
 /* y = [relu](x*scale + shift) [+ res] over n_pos positions of Cs channels (C logical). */
 int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const float* res, int relu,
                    long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);
+/* Tensor-core (tcgen05 / TMEM / TMA) variants: 3xTF32 error-compensated products, fp32 accumulate.
+ * Activations and K-major packed weights are passed as their TF32 hi / lo splits
+ * (nrgbd_split_tf32, nrgbd_pack_conv_weight_tc -> [taps][Cout_pad][Cin_pad]). Semantics otherwise
+ * identical to nrgbd_conv_nhwc / nrgbd_conv_transpose2d_k4s2_nhwc. */
+int nrgbd_conv_tc_supported(int Cin_pad, int Cout_pad);   /* Cin_pad % 32 == 0, Cout_pad % 16 == 0, <= 256 */
+int nrgbd_split_tf32(const float* x, long long n, float* hi, float* lo, nrgbd_stream_t stream);
+int nrgbd_pack_conv_weight_tc(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad,
+                              int Cout_pad, float* hi, float* lo, nrgbd_stream_t stream);
+int nrgbd_conv_nhwc_tc(const float* x_hi, const float* x_lo, int N, int Din, int Hin, int Win, int Cin_pad,
+                       int Cs_in, const float* w_hi, const float* w_lo, const float* bias, int Cout,
+                       int Cout_pad, int kd, int kh, int kw, int stride, int pad, int dilation, float* y,
+                       int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats,
+                       nrgbd_stream_t stream);
+int nrgbd_conv_transpose2d_k4s2_nhwc_tc(const float* x_hi, const float* x_lo, int N, int Hin, int Win,
+                                        int Cin_pad, int Cs_in, const float* w_hi, const float* w_lo,
+                                        const float* bias, int Cout, int Cout_pad, float* y, int Cs_out,
+                                        int c_off, int leaky, nrgbd_stream_t stream);
 /* layout / pooling helpers (P = positions per image) */
 int nrgbd_nchw_to_nhwc(const float* x, int N, int C, long long P, float* y, int Cs, int c_off,
                        nrgbd_stream_t stream);

@@ -127,3 +127,86 @@ def upsample_bilinear_ac(x, size):
     y = torch.zeros((N, size[0], size[1], pad4(C)), device=x.device, dtype=torch.float32)
     check(L.nrgbd_upsample_bilinear_ac_nhwc(ptr(xc), N, H, W, xc.shape[-1], C, ptr(y), size[0], size[1], pad4(C), 0, _st()))
     return from_cl(y, C)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) variants
+# ---------------------------------------------------------------------------------------------
+def pad_to(c, m):
+    return (c + m - 1) // m * m
+
+
+def to_cl_padded(x, Cs):
+    """[N,C,(D,)H,W] -> channels-last with an explicit channel stride Cs (zero pad channels)."""
+    L = _lib.lib()
+    N, C = x.shape[0], x.shape[1]
+    P = 1
+    for s in x.shape[2:]:
+        P *= s
+    y = torch.zeros((N,) + tuple(x.shape[2:]) + (Cs,), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_nchw_to_nhwc(ptr(x.float().contiguous()), N, C, P, ptr(y), Cs, 0, _st()))
+    return y
+
+
+def split_tf32(x):
+    L = _lib.lib()
+    hi = torch.empty_like(x); lo = torch.empty_like(x)
+    check(L.nrgbd_split_tf32(ptr(x), x.numel(), ptr(hi), ptr(lo), _st()))
+    return hi, lo
+
+
+def pack_weight_tc(w, transposed=False):
+    L = _lib.lib()
+    if transposed:
+        Cin, Cout = w.shape[0], w.shape[1]
+    else:
+        Cout, Cin = w.shape[0], w.shape[1]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    Cin_pad, Cout_pad = pad_to(Cin, 32), pad_to(Cout, 16)
+    hi = torch.empty((taps, Cout_pad, Cin_pad), device=w.device, dtype=torch.float32); lo = torch.empty_like(hi)
+    check(L.nrgbd_pack_conv_weight_tc(ptr(w.float().contiguous()), 1 if transposed else 0, Cout, Cin, taps, Cin_pad, Cout_pad,
+                                      ptr(hi), ptr(lo), _st()))
+    return hi, lo
+
+
+def conv_tc(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stats=False):
+    """Tensor-core counterpart of conv() (same arguments / returns)."""
+    L = _lib.lib()
+    is3d = x.dim() == 5
+    N = x.shape[0]
+    Din = x.shape[2] if is3d else 1
+    Hin, Win = x.shape[-2], x.shape[-1]
+    Cout, Cin = w.shape[0], w.shape[1]
+    Cin_pad, Cout_pad = pad_to(Cin, 32), pad_to(Cout, 16)
+    xc = to_cl_padded(x, Cin_pad)
+    xh, xl = split_tf32(xc)
+    kd = w.shape[2] if is3d else 1
+    kh, kw = w.shape[-2], w.shape[-1]
+    Ho = (Hin + 2 * pad - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (Win + 2 * pad - dilation * (kw - 1) - 1) // stride + 1
+    wh, wl = pack_weight_tc(w)
+    Cs_out = pad4(Cout)
+    y = torch.zeros((N,) + ((Din,) if is3d else ()) + (Ho, Wo, Cs_out), device=x.device, dtype=torch.float32)
+    stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float64) if want_stats else None
+    check(L.nrgbd_conv_nhwc_tc(ptr(xh), ptr(xl), N, Din, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout, Cout_pad,
+                               kd, kh, kw, stride, pad, dilation, ptr(y), Ho, Wo, Cs_out, 0, 1 if leaky else 0,
+                               ctypes.c_void_p(stats.data_ptr()) if want_stats else None, _st()))
+    out = from_cl(y, Cout)
+    return (out, stats) if want_stats else out
+
+
+def conv_transpose2d_tc(x, w, bias=None, leaky=False):
+    L = _lib.lib()
+    N, Cin, Hin, Win = x.shape
+    Cout = w.shape[1]
+    Cin_pad, Cout_pad = pad_to(Cin, 32), pad_to(Cout, 16)
+    xc = to_cl_padded(x, Cin_pad)
+    xh, xl = split_tf32(xc)
+    wh, wl = pack_weight_tc(w, transposed=True)
+    Cs_out = pad4(Cout)
+    y = torch.zeros((N, 2 * Hin, 2 * Win, Cs_out), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_conv_transpose2d_k4s2_nhwc_tc(ptr(xh), ptr(xl), N, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout,
+                                                Cout_pad, ptr(y), Cs_out, 0, 1 if leaky else 0, _st()))
+    return from_cl(y, Cout)

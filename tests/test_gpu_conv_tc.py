@@ -1,0 +1,94 @@
+"""GPU parity of the tcgen05 3xTF32 convolution path against the fp32 numpy oracle, op level.
+Expected error of the error-compensated product: ~2^-22 relative per term (vs 2^-11 for plain
+TF32), i.e. the same order as an fp32 FFMA chain; gate 4e-6 relative to the output scale."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kvnet_oracle as N
+from tests.conftest import maxabs
+
+pytestmark = pytest.mark.gpu
+dev = 'cuda:0'
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)     # noqa: E731
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_split_tf32_is_exact_to_22_bits():
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(0)
+    x = (rng.standard_normal(4096) * np.exp(rng.uniform(-6, 6, 4096))).astype(np.float32)
+    hi, lo = convops.split_tf32(T(x))
+    hi = hi.cpu().numpy(); lo = lo.cpu().numpy()
+    assert (hi.view(np.uint32) & 0x1FFF).max() == 0 and (lo.view(np.uint32) & 0x1FFF).max() == 0
+    assert np.abs((hi.astype(np.float64) + lo) - x).max() <= np.abs(x).max() * 2.0 ** -21
+    assert (np.abs((hi.astype(np.float64) + lo) - x) <= np.abs(x) * 2.0 ** -21).all()
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(N=1, Cin=32, Cout=32, H=8, W=16, k=1, s=1, p=0, d=1),       # one tile, one K-step
+    dict(N=1, Cin=64, Cout=64, H=8, W=16, k=1, s=1, p=0, d=1),       # two K-steps
+    dict(N=1, Cin=32, Cout=64, H=16, W=32, k=3, s=1, p=1, d=1),      # taps + halo zero fill
+    dict(N=2, Cin=64, Cout=64, H=30, W=40, k=3, s=1, p=1, d=1),      # ragged tiles (layer2 shape)
+    dict(N=1, Cin=128, Cout=128, H=20, W=28, k=3, s=1, p=2, d=2),    # layer4 dilation 2
+    dict(N=2, Cin=32, Cout=64, H=32, W=48, k=3, s=2, p=1, d=1),      # layer2.0.conv1 stride 2
+    dict(N=2, Cin=32, Cout=64, H=32, W=48, k=1, s=2, p=0, d=1),      # layer2.0.downsample
+    dict(N=1, Cin=320, Cout=128, H=16, W=24, k=3, s=1, p=1, d=1),    # lastconv.0
+    dict(N=1, Cin=96, Cout=96, H=24, W=32, k=3, s=1, p=1, d=1),      # R-Net conv1
+    dict(N=1, Cin=67, Cout=67, H=24, W=36, k=3, s=1, p=1, d=1),      # R-Net conv2 (padded to 96 / 80)
+    dict(N=3, Cin=128, Cout=32, H=1, W=2, k=1, s=1, p=0, d=1),       # SPP branch on a 1x2 map
+])
+def test_conv2d_tc_vs_oracle(cfg):
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(1)
+    x = rng.standard_normal((cfg['N'], cfg['Cin'], cfg['H'], cfg['W'])).astype(np.float32)
+    w = (rng.standard_normal((cfg['Cout'], cfg['Cin'], cfg['k'], cfg['k'])) / math.sqrt(cfg['Cin'] * cfg['k'] ** 2)).astype(np.float32)
+    b = rng.standard_normal(cfg['Cout']).astype(np.float32)
+    y, st = convops.conv_tc(T(x), T(w), T(b), cfg['s'], cfg['p'], cfg['d'], leaky=True, want_stats=True)
+    torch.cuda.synchronize()
+    ref = N.leaky_relu(N.conv2d(x, w, b, cfg['s'], cfg['p'], cfg['d']))
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu().numpy(), ref) <= 4e-6
+    st = st.cpu().numpy()
+    assert np.allclose(st[0], ref.sum(axis=(0, 2, 3), dtype=np.float64), rtol=1e-5, atol=1e-4)
+    assert np.allclose(st[1], np.square(ref.astype(np.float64)).sum(axis=(0, 2, 3)), rtol=1e-5, atol=1e-4)
+
+
+def test_conv3d_tc_vs_oracle():
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(2)
+    for cin, cout in ((16, 64), (64, 64), (64, 1)):
+        x = rng.standard_normal((1, cin, 9, 14, 18)).astype(np.float32)
+        w = (rng.standard_normal((cout, cin, 3, 3, 3)) / math.sqrt(cin * 27)).astype(np.float32)
+        y = convops.conv_tc(T(x), T(w), None, 1, 1, 1)
+        ref = N.conv3d(x, w)
+        assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 4e-6
+
+
+def test_conv_transpose2d_tc_vs_oracle():
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(3)
+    for cin, cout, h, w_ in ((128, 64, 9, 13), (96, 64, 16, 20)):
+        x = rng.standard_normal((1, cin, h, w_)).astype(np.float32)
+        w = (rng.standard_normal((cin, cout, 4, 4)) / math.sqrt(cin * 4)).astype(np.float32)
+        b = rng.standard_normal(cout).astype(np.float32)
+        y = convops.conv_transpose2d_tc(T(x), T(w), T(b), leaky=True)
+        ref = N.leaky_relu(N.conv_transpose2d(x, w, b, 2, 1))
+        assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 4e-6
+
+
+def test_tc_matches_fp32_simt_path():
+    """The two conv paths of the engine agree to fp32 rounding on the same input."""
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(4)
+    x = rng.standard_normal((2, 64, 24, 40)).astype(np.float32)
+    w = (rng.standard_normal((64, 64, 3, 3)) / 24.0).astype(np.float32)
+    a = convops.conv(T(x), T(w), None, 1, 1, 1).cpu().numpy()
+    b = convops.conv_tc(T(x), T(w), None, 1, 1, 1).cpu().numpy()
+    assert rel_err(b, a) <= 4e-6
