@@ -182,6 +182,7 @@ def run_engine(args):
         sd = arch.synth_state_dict(5, 64, D_PLANES, 2, 64)
         model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     model = model.to(dev)
+    model.conv_math = args.conv_math
     sharding.broadcast_module(model, src=0)
 
     n_win = 4
@@ -281,8 +282,8 @@ def run_engine(args):
         line = {
             'metric': 'depth frames/sec at 640x480x64-plane x4-view', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
             'steps': K, 'warmup': Wm, 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG], 'parallelism': 'dp%d (frames sharded, weights NCCL-broadcast once)' % world,
+            'vs_baseline': None, 'dtype': 'f32' if args.conv_math == 'fp32' else 'f32 (3xTF32 error-compensated tensor-core products, fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'conv_math': args.conv_math, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG], 'parallelism': 'dp%d (frames sharded, weights NCCL-broadcast once)' % world,
                        'l2': 'explicit 256 MiB flush write before every step (inside the timed region)',
                        'weights': 'random init of the reference architecture (arch.synth_state_dict seed 5)',
                        'sweep': {'avg_us': 1e3 * sw_ms / max(sw_n, 1), 'algorithmic_GBps': sweep_gbs, 'frac_of_hbm_peak': sweep_gbs / peaks['hbm_gbs'],
@@ -292,7 +293,7 @@ def run_engine(args):
             'gpu_launches': launches,
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': conv_tflops, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': conv_tflops / peak_tf,
-                         'traffic': None, 'kernel': 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM, %d launches/step, avg %.1f us)' % (conv_n // max(K, 1), 1e3 * conv_ms / max(conv_n, 1)),
+                         'traffic': None, 'kernel': ('conv_tc_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)' if args.conv_math == 'tf32x3' else 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)') + ', %d launches/step, avg %.1f us' % (conv_n // max(K, 1), 1e3 * conv_ms / max(conv_n, 1)),
                          'peak_source': peaks['source'] + ', sustained bf16'},
         }
         # cpu baseline: bounded sample of the same workload through the oracle port (rank 0, N = 1 only)
@@ -313,6 +314,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--conv-math', default='tf32x3', choices=['fp32', 'tf32x3'],
+                    help='fp32: exact CUDA-core FFMA implicit GEMM; tf32x3: tcgen05 error-compensated 3xTF32 (default)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'engine' else args.warmup
     if args.impl == 'reference':

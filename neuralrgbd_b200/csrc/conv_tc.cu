@@ -37,7 +37,7 @@ struct TcParams {
   int cin_chunks, n_taps, in_stride;
   int Cout, Cout_pad;
   int Dout, Hout, Wout, Cs_out, c_off, out_stride, out_off_y, out_off_x;
-  int leaky, stages, tmem_cols;
+  int leaky, stages, tmem_cols, nacc;
   signed char dz[MAX_TAPS_TC], dy[MAX_TAPS_TC], dx[MAX_TAPS_TC];
   unsigned char wsel[MAX_TAPS_TC];
 };
@@ -168,15 +168,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         mbar_wait(bar_full + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * stage_bytes;
+        // Accumulator plan (tensor-core fp32 accumulation truncates, so long chains drift):
+        //   columns [i*BN, (i+1)*BN), i < nacc : a_hi*b_hi of the K-steps with ks % nacc == i
+        //   columns [nacc*BN, (nacc+1)*BN)     : the two small cross terms of every K-step
+        // The epilogue adds them in fp32 with round-to-nearest.
+        const int ai = ks % p.nacc;
+        const uint32_t d_main = tmem_base + (uint32_t)(ai * BN);
+        const uint32_t d_lo = tmem_base + (uint32_t)(p.nacc * BN);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 8; ++k4) {
           const uint64_t a_hi = umma_desc_sw128(sa + k4 * 32);
           const uint64_t a_lo = umma_desc_sw128(sa + A_TILE_BYTES + k4 * 32);
           const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES + k4 * 32);
           const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_tile_bytes + k4 * 32);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, (ks > 0 || k4 > 0) ? 1u : 0u);     // small terms first
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          umma_tf32(d_lo, a_lo, b_hi, idesc, (ks > 0 || k4 > 0) ? 1u : 0u);
+          umma_tf32(d_lo, a_hi, b_lo, idesc, 1u);
+          umma_tf32(d_main, a_hi, b_hi, idesc, (ks >= p.nacc || k4 > 0) ? 1u : 0u);
         }
         umma_commit(bar_empty + 8 * s);           // frees the smem stage once these MMAs have read it
       }
@@ -197,18 +204,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool vec_ok = ((p.Cs_out | p.c_off) & 3) == 0;
     for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float accv[16];
+      const int n_used = nk < p.nacc ? nk : p.nacc;
+#pragma unroll 1
+      for (int ai = -1; ai < n_used; ++ai) {            // -1: the cross-term accumulator first (small terms)
+        uint32_t v[16];
+        const uint32_t col = (uint32_t)((ai < 0 ? p.nacc : ai) * BN + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) accv[j] = ai < 0 ? __uint_as_float(v[j]) : accv[j] + __uint_as_float(v[j]);
+      }
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(v[j]);
+        float x = accv[j];
         const int co = c0 + j;
         if (p.bias && co < p.Cout) x += __ldg(p.bias + co);
         if (p.leaky) x = x >= 0.f ? x : x * 0.01f;
@@ -285,6 +300,8 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int kind, int
   hi[i] = h; lo[i] = __uint_as_float(lb);
 }
 
+int g_force_nacc = 0;      // development knob (nrgbd_conv_tc_set_nacc): cap on the main accumulators
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -336,7 +353,13 @@ int launch_tc(const float* x_hi, const float* x_lo, int N, int Din, int Hin, int
   if (rc != NRGBD_OK) return rc;
   p.cin_chunks = Cin_pad / BK;
   p.tiles_x = ceil_div(p.Wx, TW); p.tiles_y = ceil_div(p.Hy, TH);
-  int cols = 32; while (cols < p.Cout_pad) cols <<= 1;
+  int nacc = 512 / p.Cout_pad - 1;
+  if (nacc > 4) nacc = 4;
+  if (nacc < 1) nacc = 1;
+  if (g_force_nacc > 0 && g_force_nacc < nacc) nacc = g_force_nacc;
+  p.nacc = nacc;
+  int cols = 32; while (cols < (nacc + 1) * p.Cout_pad) cols <<= 1;
+  if (cols > 512) { nrgbd_set_error("conv_tc: accumulators do not fit TMEM"); return NRGBD_ERR_UNSUPPORTED; }
   p.tmem_cols = cols;
   const size_t stage = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.Cout_pad * BK * 4;
   int stages = (int)((220 * 1024 - 2048) / stage);
@@ -360,6 +383,8 @@ int launch_tc(const float* x_hi, const float* x_lo, int N, int Din, int Hin, int
 }  // namespace
 
 extern "C" {
+
+void nrgbd_conv_tc_set_nacc(int n) { g_force_nacc = n; }
 
 // Whether the tensor-core path can run a convolution with these channel counts.
 int nrgbd_conv_tc_supported(int Cin_pad, int Cout_pad) {

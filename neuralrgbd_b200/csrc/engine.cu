@@ -48,6 +48,7 @@ struct Pool {           // stream-ordered reuse of cudaMalloc'd blocks (single s
 
 struct ParamRef { float* p; long long n; bool owned; };
 struct Packed { float* w; int Cin, Cin_pad, Cout, Cout_pad, taps; };
+struct PackedTc { float* hi; float* lo; int Cin_pad, Cout_pad, taps; };
 
 struct Camera {
   bool set = false;
@@ -57,6 +58,8 @@ struct Camera {
 };
 
 inline int pad4(int c) { return (c + 3) / 4 * 4; }
+inline int pad16(int c) { return (c + 15) / 16 * 16; }
+inline int pad32(int c) { return (c + 31) / 32 * 32; }
 
 }  // namespace
 
@@ -68,6 +71,8 @@ struct nrgbd_kvnet {
   int bn_update_running = 1;
   std::unordered_map<std::string, ParamRef> params;
   std::unordered_map<std::string, Packed> packed;
+  std::unordered_map<std::string, PackedTc> packed_tc;
+  int conv_math = 0;                // 0: exact fp32 FFMA implicit GEMM; 1: tcgen05 3xTF32 where supported
   bool packed_dirty = true;
   Camera cam[2];
   float* d_planes = nullptr;
@@ -118,7 +123,8 @@ struct ProfScope {
 };
 
 Act acquire(Eng* e, int N, int D, int H, int W, int C, int Cs = -1) {
-  Act a; a.N = N; a.D = D; a.H = H; a.W = W; a.C = C; a.Cs = Cs < 0 ? pad4(C) : Cs;
+  Act a; a.N = N; a.D = D; a.H = H; a.W = W; a.C = C;
+  a.Cs = Cs >= 0 ? Cs : ((e->conv_math == 1 && C >= 16) ? pad32(C) : pad4(C));   // tensor-core K-steps are 32 channels
   if (e->rc) return a;
   a.p = e->pool.acquire((size_t)a.floats() * sizeof(float));
   if (!a.p) { nrgbd_set_error("engine: out of device memory (%lld floats)", a.floats()); e->rc = NRGBD_ERR_NOMEM; return a; }
@@ -160,6 +166,40 @@ const Packed* packw(Eng* e, const std::string& name, int Cout, int Cin, int taps
   return &e->packed[name];
 }
 
+const PackedTc* packw_tc(Eng* e, const std::string& name, int Cout, int Cin, int taps, bool transposed) {
+  auto it = e->packed_tc.find(name);
+  if (it != e->packed_tc.end()) return &it->second;
+  float* src = param(e, name);
+  if (!src) return nullptr;
+  auto pr = e->params[name];
+  if (pr.n != (long long)Cout * Cin * taps) {
+    if (e->rc == 0) { nrgbd_set_error("engine: parameter '%s' has %lld elements, expected %lld", name.c_str(), pr.n, (long long)Cout * Cin * taps); e->rc = NRGBD_ERR_BAD_ARG; }
+    return nullptr;
+  }
+  PackedTc pk; pk.taps = taps; pk.Cin_pad = pad32(Cin); pk.Cout_pad = pad16(Cout);
+  size_t bytes = (size_t)taps * pk.Cin_pad * pk.Cout_pad * sizeof(float);
+  void* q = nullptr; void* r = nullptr;
+  if (cudaMalloc(&q, bytes) != cudaSuccess || cudaMalloc(&r, bytes) != cudaSuccess) { e->rc = NRGBD_ERR_NOMEM; nrgbd_set_error("engine: cudaMalloc failed for packed weight"); return nullptr; }
+  pk.hi = (float*)q; pk.lo = (float*)r;
+  ENG_CALL(e, nrgbd_pack_conv_weight_tc(src, transposed ? 1 : 0, Cout, Cin, taps, pk.Cin_pad, pk.Cout_pad, pk.hi, pk.lo, (nrgbd_stream_t)e->st));
+  e->packed_tc[name] = pk;
+  return &e->packed_tc[name];
+}
+
+bool use_tc(Eng* e, const Act& x, int Cout) {
+  return e->conv_math == 1 && nrgbd_conv_tc_supported(pad32(x.C), pad16(Cout)) && pad32(x.C) <= x.Cs;
+}
+
+// TF32 hi / lo split of an activation into two pool buffers
+void split_act(Eng* e, const Act& x, Act& hi, Act& lo) {
+  hi = x; lo = x; hi.p = lo.p = nullptr;
+  if (e->rc) return;
+  hi.p = e->pool.acquire((size_t)x.floats() * sizeof(float));
+  lo.p = e->pool.acquire((size_t)x.floats() * sizeof(float));
+  if (!hi.p || !lo.p) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return; }
+  ENG_CALL(e, nrgbd_split_tf32(x.p, x.floats(), hi.p, lo.p, (nrgbd_stream_t)e->st));
+}
+
 // conv (2-D when x.D == 1 and kd == 1) into a fresh activation or into `dst` at channel c_off
 Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k, int stride, int pad, int dil,
          const char* bias_name, bool leaky, bool want_stats, Act* dst = nullptr, int c_off = 0, int out_Cs = -1) {
@@ -167,11 +207,26 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   int Wo = (x.W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
   Act y;
   if (dst) y = *dst; else y = acquire(e, x.N, x.D, Ho, Wo, Cout, out_Cs);
-  const Packed* pk = packw(e, wname, Cout, x.C, kd * k * k, false);
   float* b = bias_name ? param(e, bias_name) : nullptr;
   if (e->rc) return y;
   if (want_stats) cudaMemsetAsync(e->stats, 0, sizeof(double) * 2 * Cout, e->st);
-  ProfScope ps(e, 0, 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k);
+  const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
+  if (use_tc(e, x, Cout)) {
+    const PackedTc* pt = packw_tc(e, wname, Cout, x.C, kd * k * k, false);
+    Act xh, xl;
+    split_act(e, x, xh, xl);
+    if (!e->rc) {
+      ProfScope ps(e, 0, flops);
+      ENG_CALL(e, nrgbd_conv_nhwc_tc(xh.p, xl.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
+                                     stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
+                                     (nrgbd_stream_t)e->st));
+    }
+    release(e, xh); release(e, xl);
+    return y;
+  }
+  const Packed* pk = packw(e, wname, Cout, x.C, kd * k * k, false);
+  if (e->rc) return y;
+  ProfScope ps(e, 0, flops);
   ENG_CALL(e, nrgbd_conv_nhwc(x.p, x.N, x.D, x.H, x.W, pk->Cin_pad, x.Cs, pk->w, b, Cout, pk->Cout_pad, kd, k, k, stride,
                               pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
                               (nrgbd_stream_t)e->st));
@@ -263,42 +318,56 @@ void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
   release(e, raw); release(e, skip);
   Act lc = convbn(e, cat, P + ".lastconv.0", 128, 1, 3, 1, 1, 1, true, nullptr);
   release(e, cat);
-  feat_out = conv(e, lc, P + ".lastconv.2.weight", e->F, 1, 1, 1, 0, 1, nullptr, false, false);
+  feat_out = conv(e, lc, P + ".lastconv.2.weight", e->F, 1, 1, 1, 0, 1, nullptr, false, false, nullptr, 0, pad4(e->F));   // dense: the sweep's wide layout
   release(e, lc);
   l1_out = l1;
 }
 
+// ConvTranspose2d(k4, s2, p1) + bias + LeakyReLU into channels [0, Cout) of dst
+void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* bias_name, int Cout, Act& dst) {
+  float* tb = param(e, bias_name);
+  if (e->rc) return;
+  nrgbd_stream_t st = (nrgbd_stream_t)e->st;
+  const double flops = 2.0 * 4.0 * (double)x.H * x.W * Cout * x.C * 4;
+  if (use_tc(e, x, Cout)) {
+    const PackedTc* pt = packw_tc(e, wname, Cout, x.C, 16, true);
+    Act xh, xl;
+    split_act(e, x, xh, xl);
+    if (!e->rc) {
+      ProfScope ps(e, 0, flops);
+      ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc_tc(xh.p, xl.p, x.N, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, tb, Cout, pt->Cout_pad,
+                                                      dst.p, dst.Cs, 0, 1, st));
+    }
+    release(e, xh); release(e, xl);
+    return;
+  }
+  const Packed* pk = packw(e, wname, Cout, x.C, 16, true);
+  if (e->rc) return;
+  ProfScope ps(e, 0, flops);
+  ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc(x.p, x.N, x.H, x.W, pk->Cin_pad, x.Cs, pk->w, tb, Cout, pk->Cout_pad, dst.p, dst.Cs, 0, 1, st));
+}
+
 // models/Refine.py:79-107. prob source: log-DPV pixel-major [hw][D]; returns log-DPV [H*W][D].
-Act r_net(Eng* e, const float* bv_hwd, const float* feat_ref, const float* l1_ref, const Act& frame_ref) {
+Act r_net(Eng* e, const float* bv_hwd, const float* feat_ref, int feat_Cs, const float* l1_ref, int l1_Cs, const Act& frame_ref) {
   const int D = e->D, h = e->h, w = e->w, H = e->H, W = e->W, F = e->F;
   const long long hw = (long long)h * w;
   nrgbd_stream_t st = (nrgbd_stream_t)e->st;
   Act in0 = acquire(e, 1, 1, h, w, D + F);
   if (!e->rc) {
     ENG_CALL(e, nrgbd_copy_channels(bv_hwd, hw, D, 0, D, 1, in0.p, in0.Cs, 0, st));           // torch.exp(BV)
-    ENG_CALL(e, nrgbd_copy_channels(feat_ref, hw, pad4(F), 0, F, 0, in0.p, in0.Cs, D, st));
+    ENG_CALL(e, nrgbd_copy_channels(feat_ref, hw, feat_Cs, 0, F, 0, in0.p, in0.Cs, D, st));
   }
   Act a = conv(e, in0, "r_net.conv0.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0.0.bias", true, false); release(e, in0);
   Act b = conv(e, a, "r_net.conv0_1.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0_1.0.bias", true, false); release(e, a);
   Act t0 = acquire(e, 1, 1, 2 * h, 2 * w, D + F / 2);
-  const Packed* pk = packw(e, "r_net.trans_conv0.0.weight", D, D + F, 16, true);
-  float* tb = param(e, "r_net.trans_conv0.0.bias");
-  if (!e->rc) {
-    ProfScope ps(e, 0, 2.0 * 4.0 * hw * D * (D + F) * 4);
-    ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc(b.p, 1, h, w, pk->Cin_pad, b.Cs, pk->w, tb, D, pk->Cout_pad, t0.p, t0.Cs, 0, 1, st));
-    ENG_CALL(e, nrgbd_copy_channels(l1_ref, 4 * hw, pad4(F / 2), 0, F / 2, 0, t0.p, t0.Cs, D, st));
-  }
+  conv_transpose(e, b, "r_net.trans_conv0.0.weight", "r_net.trans_conv0.0.bias", D, t0);
+  if (!e->rc) ENG_CALL(e, nrgbd_copy_channels(l1_ref, 4 * hw, l1_Cs, 0, F / 2, 0, t0.p, t0.Cs, D, st));
   release(e, b);
   Act c = conv(e, t0, "r_net.conv1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1.0.bias", true, false); release(e, t0);
   Act d = conv(e, c, "r_net.conv1_1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1_1.0.bias", true, false); release(e, c);
   Act t1 = acquire(e, 1, 1, H, W, D + 3);
-  pk = packw(e, "r_net.trans_conv1.0.weight", D, D + F / 2, 16, true);
-  tb = param(e, "r_net.trans_conv1.0.bias");
-  if (!e->rc) {
-    ProfScope ps(e, 0, 2.0 * 16.0 * hw * D * (D + F / 2) * 4);
-    ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc(d.p, 1, 2 * h, 2 * w, pk->Cin_pad, d.Cs, pk->w, tb, D, pk->Cout_pad, t1.p, t1.Cs, 0, 1, st));
-    ENG_CALL(e, nrgbd_copy_channels(frame_ref.p, (long long)H * W, frame_ref.Cs, 0, 3, 0, t1.p, t1.Cs, D, st));
-  }
+  conv_transpose(e, d, "r_net.trans_conv1.0.weight", "r_net.trans_conv1.0.bias", D, t1);
+  if (!e->rc) ENG_CALL(e, nrgbd_copy_channels(frame_ref.p, (long long)H * W, frame_ref.Cs, 0, 3, 0, t1.p, t1.Cs, D, st));
   release(e, d);
   Act f = conv(e, t1, "r_net.conv2.0.weight", D + 3, 1, 3, 1, 1, 1, "r_net.conv2.0.bias", true, false); release(e, t1);
   Act g = conv(e, f, "r_net.conv2_1.0.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_1.0.bias", true, false); release(e, f);
@@ -371,6 +440,7 @@ int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
   if (!e) return NRGBD_OK;
   for (auto& kv : e->params) if (kv.second.owned) cudaFree(kv.second.p);
   for (auto& kv : e->packed) cudaFree(kv.second.w);
+  for (auto& kv : e->packed_tc) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
   for (int i = 0; i < 2; ++i) { cudaFree(e->cam[i].K); cudaFree(e->cam[i].rays); }
   cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
   cudaFree(e->bv_cur_hwd); cudaFree(e->dpv_hwd); cudaFree(e->prior_hwd); cudaFree(e->depth); cudaFree(e->conf);
@@ -397,6 +467,8 @@ int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, l
   }
   auto pk = e->packed.find(key);
   if (pk != e->packed.end()) { cudaFree(pk->second.w); e->packed.erase(pk); }
+  auto pt = e->packed_tc.find(key);
+  if (pt != e->packed_tc.end()) { cudaFree(pt->second.hi); cudaFree(pt->second.lo); e->packed_tc.erase(pt); }
   ParamRef r; r.n = n; r.owned = !is_device;
   if (is_device) {
     r.p = const_cast<float*>(data);
@@ -441,6 +513,10 @@ int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value) {
   std::string k(key);
   if (k == "bn_update_running") { e->bn_update_running = value; return NRGBD_OK; }
   if (k == "profile") { e->profile = value; return NRGBD_OK; }
+  if (k == "conv_math") {            // 0: exact fp32 (CUDA cores); 1: tcgen05 3xTF32 (tensor cores)
+    if (value != 0 && value != 1) { nrgbd_set_error("conv_math must be 0 (fp32) or 1 (tf32x3)"); return NRGBD_ERR_BAD_ARG; }
+    e->conv_math = value; return NRGBD_OK;
+  }
   nrgbd_set_error("nrgbd_kvnet_set_option: unknown option '%s'", key);
   return NRGBD_ERR_BAD_ARG;
 }
@@ -525,7 +601,7 @@ int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses,
   Act frame_ref = x0; frame_ref.N = 1; frame_ref.p = x0.p ? x0.p + (size_t)V * HW * x0.Cs : nullptr;
   const bool steady = bv_predict != nullptr;
   if (dmap_cur_refined || (!steady && dmap_refined)) {
-    Act r = r_net(e, e->bv_cur_hwd, feat_ref, l1_ref, frame_ref);
+    Act r = r_net(e, e->bv_cur_hwd, feat_ref, feat.Cs, l1_ref, l1.Cs, frame_ref);
     if (dmap_cur_refined) ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_cur_refined, st));
     if (!steady && dmap_refined) ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_refined, st));
     release(e, r);
@@ -539,7 +615,7 @@ int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses,
     const Camera& c1 = e->cam[1];
     const int CK = 3 * V + 4;
     ENG_CALL(e, nrgbd_transpose2d(bv_predict, D, (int)hw, e->prior_hwd, st));
-    Act vol = acquire(e, 1, D, h, w, CK, pad4(CK));
+    Act vol = acquire(e, 1, D, h, w, CK);
     ENG_CALL(e, nrgbd_knet_input_volume(rgbq.p, rgbq.p + (size_t)V * hw * 4, e->bv_cur_hwd, e->prior_hwd, V, D, h, w, vol.Cs,
                                         c1.K, Rs, ts, c1.rays, e->d_planes, c1.cx, c1.cy, e->ws_sweep, vol.p, st));
     Act gain = kv_net(e, vol);
@@ -550,7 +626,7 @@ int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses,
     release(e, gain);
     if (dpv) ENG_CALL(e, nrgbd_transpose2d(e->dpv_hwd, (int)hw, D, dpv, st));
     if (dmap_refined) {
-      Act r = r_net(e, e->dpv_hwd, feat_ref, l1_ref, frame_ref);
+      Act r = r_net(e, e->dpv_hwd, feat_ref, feat.Cs, l1_ref, l1.Cs, frame_ref);
       ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_refined, st));
       release(e, r);
     }

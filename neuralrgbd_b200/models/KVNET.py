@@ -91,6 +91,7 @@ class KVNET(nn.Module):
         self.if_upsample_d = if_upsample_d
         self.cam_intrinsics = cam_intrinsics          # captured at construction: used by D-Net (KVNET.py:64-67)
         self.feat_dist = 'L2'                         # basic.py:146 default, never overridden by KVNET
+        self.conv_math = 'fp32'                       # 'fp32' (exact CUDA-core FFMA) | 'tf32x3' (tcgen05 tensor cores)
 
         D = len(d_candi)
         gen = torch.Generator().manual_seed(0)
@@ -122,7 +123,7 @@ class KVNET(nn.Module):
                                        ctypes.byref(hnd)))
             d32 = np.ascontiguousarray(np.asarray(self.d_candi).astype(np.float32))
             check(L.nrgbd_kvnet_set_planes(hnd, d32.ctypes.data_as(ctypes.c_void_p), len(d32)))
-            ent = {'h': hnd, 'params': {}, 'cams': [None, None], 'keep': {}}
+            ent = {'h': hnd, 'params': {}, 'cams': [None, None], 'keep': {}, 'conv_math': None}
             self._engines[key] = ent
         return ent
 
@@ -195,6 +196,11 @@ class KVNET(nn.Module):
             D = len(self.d_candi)
             ent = self._engine(H, W, V, dev)
             self._sync_params(ent, dev)
+            if ent['conv_math'] != self.conv_math:
+                if self.conv_math not in ('fp32', 'tf32x3'):
+                    raise ValueError("conv_math must be 'fp32' or 'tf32x3'")
+                check(L.nrgbd_kvnet_set_option(ent['h'], b'conv_math', 1 if self.conv_math == 'tf32x3' else 0))
+                ent['conv_math'] = self.conv_math
             self._set_camera(ent, 0, cam=self.cam_intrinsics)
             prior = None
             if isinstance(BV_predict, torch.Tensor) and m_misc.valid_dpv(BV_predict):
