@@ -142,6 +142,10 @@ int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const
  * identical to nrgbd_conv_nhwc / nrgbd_conv_transpose2d_k4s2_nhwc. */
 int nrgbd_conv_tc_supported(int Cin_pad, int Cout_pad);   /* Cin_pad % 32 == 0, Cout_pad % 16 == 0, <= 256 */
 void nrgbd_conv_tc_set_nacc(int n);  /* development knob: cap on the rotating main accumulators (0 = auto) */
+void nrgbd_conv_tc_set_dev(int stages, int flags); /* development knobs: pipeline depth cap; flags bit0 = plain 1xTF32 */
+void nrgbd_conv_tc_set_debug_buffer(long long* device_buf); /* development: [grid][8] clock64 stamps of the v1 kernel */
+int nrgbd_mma_probe(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, int n_ctas, long long* out,
+                    nrgbd_stream_t stream);   /* development: raw tcgen05.mma rate probe */
 int nrgbd_split_tf32(const float* x, long long n, float* hi, float* lo, nrgbd_stream_t stream);
 int nrgbd_pack_conv_weight_tc(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad,
                               int Cout_pad, float* hi, float* lo, nrgbd_stream_t stream);
@@ -154,6 +158,17 @@ int nrgbd_conv_transpose2d_k4s2_nhwc_tc(const float* x_hi, const float* x_lo, in
                                         int Cin_pad, int Cs_in, const float* w_hi, const float* w_lo,
                                         const float* bias, int Cout, int Cout_pad, float* y, int Cs_out,
                                         int c_off, int leaky, nrgbd_stream_t stream);
+/* v2 tensor-core kernels: raw fp32 activations (the TF32 split happens in-kernel, operand A is fed
+ * from TMEM), pre-split K-major weights. Cout_pad <= 128. Same semantics as the v1 entries. */
+int nrgbd_conv_tc2_supported(int Cin_pad, int Cout_pad);
+int nrgbd_conv_nhwc_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in,
+                        const float* w_hi, const float* w_lo, const float* bias, int Cout, int Cout_pad,
+                        int kd, int kh, int kw, int stride, int pad, int dilation, float* y, int Hout,
+                        int Wout, int Cs_out, int c_off, int leaky, double* stats, nrgbd_stream_t stream);
+int nrgbd_conv_transpose2d_k4s2_nhwc_tc2(const float* x, int N, int Hin, int Win, int Cin_pad, int Cs_in,
+                                         const float* w_hi, const float* w_lo, const float* bias, int Cout,
+                                         int Cout_pad, float* y, int Cs_out, int c_off, int leaky,
+                                         nrgbd_stream_t stream);
 /* layout / pooling helpers (P = positions per image) */
 int nrgbd_nchw_to_nhwc(const float* x, int N, int C, long long P, float* y, int Cs, int c_off,
                        nrgbd_stream_t stream);

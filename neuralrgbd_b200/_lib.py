@@ -39,6 +39,9 @@ SIGNATURES = {
                                                  c_vp, c_int, c_int, c_int, c_vp]),
     'nrgbd_conv_tc_supported': (c_int, [c_int, c_int]),
     'nrgbd_conv_tc_set_nacc': (None, [c_int]),
+    'nrgbd_conv_tc_set_dev': (None, [c_int, c_int]),
+    'nrgbd_conv_tc_set_debug_buffer': (None, [c_vp]),
+    'nrgbd_mma_probe': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'nrgbd_split_tf32': (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp]),
     'nrgbd_pack_conv_weight_tc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'nrgbd_conv_nhwc_tc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int,
@@ -46,6 +49,12 @@ SIGNATURES = {
                                    c_vp]),
     'nrgbd_conv_transpose2d_k4s2_nhwc_tc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
                                                     c_int, c_vp, c_int, c_int, c_int, c_vp]),
+    'nrgbd_conv_tc2_supported': (c_int, [c_int, c_int]),
+    'nrgbd_conv_nhwc_tc2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp,
+                                    c_vp]),
+    'nrgbd_conv_transpose2d_k4s2_nhwc_tc2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
+                                                     c_int, c_vp, c_int, c_int, c_int, c_vp]),
     'nrgbd_bn_finalize': (c_int, [c_vp, c_int, ctypes.c_double, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp,
                                   c_float, c_vp]),
     'nrgbd_bn_apply': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_vp, c_vp]),

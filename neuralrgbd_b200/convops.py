@@ -171,8 +171,9 @@ def pack_weight_tc(w, transposed=False):
     return hi, lo
 
 
-def conv_tc(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stats=False):
-    """Tensor-core counterpart of conv() (same arguments / returns)."""
+def conv_tc(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stats=False, impl='v1'):
+    """Tensor-core counterpart of conv() (same arguments / returns). impl: 'v1' (pre-split activations
+    from global memory) or 'v2' (raw activations, in-kernel split, A operand from TMEM)."""
     L = _lib.lib()
     is3d = x.dim() == 5
     N = x.shape[0]
@@ -190,14 +191,19 @@ def conv_tc(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stat
     Cs_out = pad4(Cout)
     y = torch.zeros((N,) + ((Din,) if is3d else ()) + (Ho, Wo, Cs_out), device=x.device, dtype=torch.float32)
     stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float64) if want_stats else None
-    check(L.nrgbd_conv_nhwc_tc(ptr(xh), ptr(xl), N, Din, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout, Cout_pad,
-                               kd, kh, kw, stride, pad, dilation, ptr(y), Ho, Wo, Cs_out, 0, 1 if leaky else 0,
-                               ctypes.c_void_p(stats.data_ptr()) if want_stats else None, _st()))
+    if impl == 'v2':
+        check(L.nrgbd_conv_nhwc_tc2(ptr(xc), N, Din, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout, Cout_pad,
+                                    kd, kh, kw, stride, pad, dilation, ptr(y), Ho, Wo, Cs_out, 0, 1 if leaky else 0,
+                                    ctypes.c_void_p(stats.data_ptr()) if want_stats else None, _st()))
+    else:
+        check(L.nrgbd_conv_nhwc_tc(ptr(xh), ptr(xl), N, Din, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout, Cout_pad,
+                                   kd, kh, kw, stride, pad, dilation, ptr(y), Ho, Wo, Cs_out, 0, 1 if leaky else 0,
+                                   ctypes.c_void_p(stats.data_ptr()) if want_stats else None, _st()))
     out = from_cl(y, Cout)
     return (out, stats) if want_stats else out
 
 
-def conv_transpose2d_tc(x, w, bias=None, leaky=False):
+def conv_transpose2d_tc(x, w, bias=None, leaky=False, impl='v1'):
     L = _lib.lib()
     N, Cin, Hin, Win = x.shape
     Cout = w.shape[1]
@@ -207,6 +213,10 @@ def conv_transpose2d_tc(x, w, bias=None, leaky=False):
     wh, wl = pack_weight_tc(w, transposed=True)
     Cs_out = pad4(Cout)
     y = torch.zeros((N, 2 * Hin, 2 * Win, Cs_out), device=x.device, dtype=torch.float32)
-    check(L.nrgbd_conv_transpose2d_k4s2_nhwc_tc(ptr(xh), ptr(xl), N, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout,
-                                                Cout_pad, ptr(y), Cs_out, 0, 1 if leaky else 0, _st()))
+    if impl == 'v2':
+        check(L.nrgbd_conv_transpose2d_k4s2_nhwc_tc2(ptr(xc), N, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout,
+                                                     Cout_pad, ptr(y), Cs_out, 0, 1 if leaky else 0, _st()))
+    else:
+        check(L.nrgbd_conv_transpose2d_k4s2_nhwc_tc(ptr(xh), ptr(xl), N, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout,
+                                                    Cout_pad, ptr(y), Cs_out, 0, 1 if leaky else 0, _st()))
     return from_cl(y, Cout)

@@ -28,7 +28,7 @@ constexpr int TH = 8, TW = 16;       // spatial tile: 8 rows x 16 columns = 128 
 constexpr int BK = 32;               // input channels per K-step (128 bytes = one swizzle row)
 constexpr int A_TILE_BYTES = 128 * BK * 4;
 constexpr int MAX_TAPS_TC = 27;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;      // warps: 0 TMA, 1 MMA stream 0 (+TMEM alloc), 2-5 epilogue, 6 MMA stream 1
 
 struct TcParams {
   float* y; const float* bias; double* stats;
@@ -37,18 +37,34 @@ struct TcParams {
   int cin_chunks, n_taps, in_stride;
   int Cout, Cout_pad;
   int Dout, Hout, Wout, Cs_out, c_off, out_stride, out_off_y, out_off_x;
-  int leaky, stages, tmem_cols, nacc;
+  int leaky, stages, tmem_cols, nacc, dev_flags;   // nacc: rotating main accumulators (nm)
+  int nl;                            // (unused)
+  int n_issue;                       // MMA issue streams (warps): 1 or 2
+  long long* dbg;                    // optional [grid][8] clock64 timestamps (development)
   signed char dz[MAX_TAPS_TC], dy[MAX_TAPS_TC], dx[MAX_TAPS_TC];
   unsigned char wsel[MAX_TAPS_TC];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp (cute::elect_one_sync): keeps tcgen05 / TMA issue on the
+// uniform datapath instead of a per-instruction divergence loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %1;\n\t"
+      "@%%px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  if (elect_one()) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded spin: a protocol bug becomes a trap (error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -66,12 +82,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
-  asm volatile(
+  if (elect_one()) asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
+  if (elect_one()) asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
@@ -85,14 +101,38 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Raw (un-elected) forms for use inside ONE `if (elect_one())` block per K-step: measured with
+// tools/mma_probe.py, a per-MMA elect + 64-bit descriptor construction costs ~75 issue cycles per MMA,
+// more than the tensor work of an N <= 128 MMA (16-64 cycles), so the issue stream must be lean:
+// descriptors are (constant high word, low word = stage base + immediate).
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | (uint64_t)lo; }
+__device__ __forceinline__ void umma_tf32_raw(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
+__device__ __forceinline__ void umma_tf32_ts_raw(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_raw(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -100,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const long long t_start = clock64();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int BN = p.Cout_pad;
@@ -109,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const uint32_t bar_full = bars, bar_empty = bars + 8 * p.stages, bar_tmem = bars + 16 * p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + p.stages * stage_bytes + 16 * p.stages + 8);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
 
   // tile coordinates
   int t = blockIdx.x;
@@ -120,8 +161,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int ox0 = tx * TW, oy0 = ty * TH;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_tmem, 1);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, p.n_issue); }
+    mbar_init(bar_tmem, p.n_issue);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a_lo) : "memory");
@@ -136,60 +177,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 8 + 0] = t_start; p.dbg[blockIdx.x * 8 + 1] = clock64(); }
 
   const int nk = p.n_taps * p.cin_chunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer (whole warp converged; one elected lane issues) =====
       for (int ks = 0; ks < nk; ++ks) {
         const int s = ks % p.stages;
         const uint32_t ph = (uint32_t)(ks / p.stages) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+        const bool one = (p.dev_flags & 1) != 0;
+        mbar_expect_tx(bar_full + 8 * s, one ? stage_bytes / 2 : stage_bytes);
         const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
         const uint32_t sa = smem_base + s * stage_bytes;
         const int cx = ox0 * p.in_stride + p.dx[tap], cy = oy0 * p.in_stride + p.dy[tap], cz = z0 + p.dz[tap];
         tma_load_5d(sa, &tm_a_hi, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
-        tma_load_5d(sa + A_TILE_BYTES, &tm_a_lo, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
+        if (!one) tma_load_5d(sa + A_TILE_BYTES, &tm_a_lo, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
         tma_load_3d(sa + 2 * A_TILE_BYTES, &tm_b_hi, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
-        tma_load_3d(sa + 2 * A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+        if (!one) tma_load_3d(sa + 2 * A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A/B=TF32 [7,10)/[10,13)=2,
-      // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+  } else if (warp == 1 || warp == 6) {
+    const int w = warp == 1 ? 0 : 1;
+    if (w < p.n_issue) {
+      // ===== MMA issue stream w (whole warp converged; one elected lane issues) =====
+      // One issuing warp sustains about one tcgen05.mma per ~100 cycles whatever N, the pipeline depth
+      // or the operand bytes (measured: 1320 cycles per 12-MMA K-step for N = 64 and N = 128 alike;
+      // rotating or grouping destinations does not help), while independent streams scale. So the
+      // K-slices of every K-step are divided between n_issue warps, each with its own accumulator
+      // pair so that no ordering between the streams is needed:
+      //   columns [(2w)*BN, +BN)   stream w: a_hi*b_hi        (fp32 accumulation truncates: two half-
+      //   columns [(2w+1)*BN, +BN) stream w: cross terms        length chains + RN sum in the epilogue)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      const int k_lo = w * (BK / 8) / p.n_issue, k_hi = (w + 1) * (BK / 8) / p.n_issue;
+      const uint32_t d_base = tmem_base + (uint32_t)(w * (p.nacc + 1) * BN);   // stream w: nacc rotating mains, then cross terms
+      const uint32_t d_lo = d_base + (uint32_t)(p.nacc * BN);
+      const bool one = (p.dev_flags & 1) != 0;
       for (int ks = 0; ks < nk; ++ks) {
         const int s = ks % p.stages;
         const uint32_t ph = (uint32_t)(ks / p.stages) & 1u;
         mbar_wait(bar_full + 8 * s, ph);
+        if (p.dbg && ks == 0 && lane == 0 && w == 0) p.dbg[blockIdx.x * 8 + 2] = clock64();      // first operands landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * stage_bytes;
-        // Accumulator plan (tensor-core fp32 accumulation truncates, so long chains drift):
-        //   columns [i*BN, (i+1)*BN), i < nacc : a_hi*b_hi of the K-steps with ks % nacc == i
-        //   columns [nacc*BN, (nacc+1)*BN)     : the two small cross terms of every K-step
-        // The epilogue adds them in fp32 with round-to-nearest.
-        const int ai = ks % p.nacc;
-        const uint32_t d_main = tmem_base + (uint32_t)(ai * BN);
-        const uint32_t d_lo = tmem_base + (uint32_t)(p.nacc * BN);
+        const uint32_t d_main = d_base + (uint32_t)((ks % p.nacc) * BN);        // rotates per K-step (RZ drift)
+        const uint32_t la_hi = desc_lo(sa), la_lo = desc_lo(sa + A_TILE_BYTES);
+        const uint32_t lb_hi = desc_lo(sa + 2 * A_TILE_BYTES), lb_lo = desc_lo(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 8; ++k4) {
-          const uint64_t a_hi = umma_desc_sw128(sa + k4 * 32);
-          const uint64_t a_lo = umma_desc_sw128(sa + A_TILE_BYTES + k4 * 32);
-          const uint64_t b_hi = umma_desc_sw128(sa + 2 * A_TILE_BYTES + k4 * 32);
-          const uint64_t b_lo = umma_desc_sw128(sa + 2 * A_TILE_BYTES + b_tile_bytes + k4 * 32);
-          umma_tf32(d_lo, a_lo, b_hi, idesc, (ks > 0 || k4 > 0) ? 1u : 0u);
-          umma_tf32(d_lo, a_hi, b_lo, idesc, 1u);
-          umma_tf32(d_main, a_hi, b_hi, idesc, (ks >= p.nacc || k4 > 0) ? 1u : 0u);
+          for (int k4 = 0; k4 < BK / 8; ++k4) {
+            if (k4 >= k_lo && k4 < k_hi) {
+              const uint32_t acc = (ks > 0 || k4 > k_lo) ? 1u : 0u;
+              const uint32_t acc_m = (ks >= p.nacc || k4 > k_lo) ? 1u : 0u;
+              if (!one) {
+                umma_tf32_raw(d_lo, desc_of(la_lo + 2 * k4), desc_of(lb_hi + 2 * k4), idesc, acc);
+                umma_tf32_raw(d_lo, desc_of(la_hi + 2 * k4), desc_of(lb_lo + 2 * k4), idesc, 1u);
+              } else if (ks == 0 && k4 == k_lo) {
+                umma_tf32_raw(d_lo, desc_of(la_hi + 2 * k4), desc_of(lb_hi + 2 * k4), idesc, 0u);   // 1xTF32 experiment
+              }
+              umma_tf32_raw(d_main, desc_of(la_hi + 2 * k4), desc_of(lb_hi + 2 * k4), idesc, acc_m);
+            }
+          }
+          umma_commit_raw(bar_empty + 8 * s);       // this stream is done with the smem stage
         }
-        umma_commit(bar_empty + 8 * s);           // frees the smem stage once these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(bar_tmem);                      // accumulator complete
+      umma_commit(bar_tmem);                      // this stream's accumulators are complete
+      if (p.dbg && lane == 0 && w == 0) p.dbg[blockIdx.x * 8 + 3] = clock64();      // all MMAs issued
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===== epilogue (warps 2..5): TMEM lanes [32*(warp%4), +32) =====
     const int q = warp & 3;
     const int r = q * 32 + lane;                  // GEMM row = TMEM lane = pixel within the tile
@@ -201,24 +259,303 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     float* ep = reinterpret_cast<float*>(smem_gen);          // [128][BN+1] staging, reuses the pipeline stages
     const int EPS = BN + 1;
     mbar_wait(bar_tmem, 0);
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 8 + 4] = clock64();   // accumulator complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool vec_ok = ((p.Cs_out | p.c_off) & 3) == 0;
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float accv[16];
-      const int n_used = nk < p.nacc ? nk : p.nacc;
-#pragma unroll 1
-      for (int ai = -1; ai < n_used; ++ai) {            // -1: the cross-term accumulator first (small terms)
-        uint32_t v[16];
-        const uint32_t col = (uint32_t)((ai < 0 ? p.nacc : ai) * BN + c0);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      {
+        // accumulator order: cross-term accumulators first (small), then the main chains; fetched
+        // four at a time back to back with one wait
+        const int per = p.nacc + 1;                         // accumulators per issue stream: nacc mains + cross terms
+        const int used_m = nk < p.nacc ? nk : p.nacc;       // mains actually written (rotation per K-step)
+        const int n_acc = p.n_issue * (used_m + 1);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) accv[j] = ai < 0 ? __uint_as_float(v[j]) : accv[j] + __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) accv[j] = 0.f;
+#pragma unroll 1
+        for (int a0 = 0; a0 < n_acc; a0 += 4) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (a0 + u < n_acc) {
+              const int idx = a0 + u;
+              // cross-term accumulators first (small), then the mains of every stream
+              const int slot = (idx < p.n_issue) ? idx * per + p.nacc : ((idx - p.n_issue) / used_m) * per + (idx - p.n_issue) % used_m;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0);
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                  : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]), "=r"(v[u][4]), "=r"(v[u][5]), "=r"(v[u][6]),
+                    "=r"(v[u][7]), "=r"(v[u][8]), "=r"(v[u][9]), "=r"(v[u][10]), "=r"(v[u][11]), "=r"(v[u][12]),
+                    "=r"(v[u][13]), "=r"(v[u][14]), "=r"(v[u][15])
+                  : "r"(taddr) : "memory");
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (a0 + u < n_acc) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(v[u][j]);
+            }
+        }
+      }
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = accv[j];
+        const int co = c0 + j;
+        if (p.bias && co < p.Cout) x += __ldg(p.bias + co);
+        if (p.leaky) x = x >= 0.f ? x : x * 0.01f;
+        f[j] = (valid && co < p.Cout) ? x : 0.f;
+      }
+      if (valid) {
+        if (vec_ok && c0 + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (c0 + j < p.Cout) dst[c0 + j] = f[j];
+        }
+      }
+      if (p.stats) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ep[r * EPS + c0 + j] = f[j];
+      }
+    }
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 8 + 5] = clock64();   // outputs stored
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
+      const int e = threadIdx.x - 64;                        // 0..127
+      for (int co = e; co < p.Cout; co += 128) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int rr = 0; rr < 128; ++rr) { float x = ep[rr * EPS + co]; s1 += x; s2 = fmaf(x, x, s2); }
+        atomicAdd(p.stats + co, (double)s1);
+        atomicAdd(p.stats + p.Cout + co, (double)s2);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+  if (p.dbg && threadIdx.x == 32) {
+    unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.dbg[blockIdx.x * 8 + 6] = clock64(); p.dbg[blockIdx.x * 8 + 7] = smid;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v2: in-kernel operand split, A operand from TMEM.
+// TMA brings the RAW fp32 activation box (16 KB per K-step instead of 32 KB of pre-split hi/lo:
+// the kernel is L2->SM bandwidth bound). Warps 2-5 read their pixel's 128-byte row
+// from the swizzled tile, split it in registers (cvt.rna.tf32) and tcgen05.st hi and lo into a
+// double-buffered TMEM operand region; warp 1 issues the three MMAs per K-slice with A from TMEM
+// and the pre-split K-major weights from smem. The separate split kernel and its HBM round trip
+// disappear.
+//   barriers: full[s]  TMA -> converter (A) and MMA (B)           (expect-tx)
+//             empty[s] 4 converter-warp arrivals + 1 tcgen05.commit -> TMA
+//             afull[b] 4 converter-warp arrivals -> MMA            (TMEM operand buffer b written)
+//             aempty[b] tcgen05.commit -> converter                (MMAs reading buffer b retired)
+//             tmem_full tcgen05.commit -> epilogue
+// ---------------------------------------------------------------------------------------------
+constexpr int NUM_THREADS2 = 224;
+constexpr int A_BUF_COLS = 64;                 // 32 hi + 32 lo columns per TMEM operand buffer
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31]) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi,
+                const __grid_constant__ CUtensorMap tm_b_lo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int BN = p.Cout_pad;
+  const uint32_t b_tile_bytes = (uint32_t)BN * BK * 4;
+  const uint32_t stage_bytes = A_TILE_BYTES + 2 * b_tile_bytes;
+  const uint32_t bars = smem_base + p.stages * stage_bytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * p.stages, bar_afull = bars + 16 * p.stages,
+                 bar_aempty = bar_afull + 16, bar_tmem = bar_afull + 32;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + p.stages * stage_bytes + 16 * p.stages + 40);
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; t /= p.tiles_y;
+  const int z0 = t % p.Dz;
+  const int n0 = t / p.Dz;
+  const int ox0 = tx * TW, oy0 = ty * TH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4 + p.n_issue); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_afull + 8 * b, 4); mbar_init(bar_aempty + 8 * b, p.n_issue); }
+    mbar_init(bar_tmem, p.n_issue);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t acc_cols = (uint32_t)(p.n_issue * (p.nacc + 1) * BN);   // operand buffers live after the accumulators
+  const int nk = p.n_taps * p.cin_chunks;
+
+  if (warp == 0) {
+    {
+      for (int ks = 0; ks < nk; ++ks) {
+        const int s = ks % p.stages;
+        const uint32_t ph = (uint32_t)(ks / p.stages) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+        const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const int cx = ox0 * p.in_stride + p.dx[tap], cy = oy0 * p.in_stride + p.dy[tap], cz = z0 + p.dz[tap];
+        tma_load_5d(sa, &tm_a, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
+        tma_load_3d(sa + A_TILE_BYTES, &tm_b_hi, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+        tma_load_3d(sa + A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+      }
+    }
+  } else if (warp == 1 || warp == 6) {
+    const int w = warp == 1 ? 0 : 1;
+    if (w < p.n_issue) {
+      // ===== MMA issue stream w (see conv_tc_kernel) =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      const int k_lo = w * (BK / 8) / p.n_issue, k_hi = (w + 1) * (BK / 8) / p.n_issue;
+      const uint32_t d_base = tmem_base + (uint32_t)(w * (p.nacc + 1) * BN);
+      const uint32_t d_lo = d_base + (uint32_t)(p.nacc * BN);
+      for (int ks = 0; ks < nk; ++ks) {
+        const int s = ks % p.stages, b = ks & 1;
+        const uint32_t d_main = d_base + (uint32_t)((ks % p.nacc) * BN);
+        mbar_wait(bar_full + 8 * s, (uint32_t)(ks / p.stages) & 1u);        // weights landed
+        mbar_wait(bar_afull + 8 * b, (uint32_t)(ks >> 1) & 1u);             // operand buffer b written
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint32_t a_hi0 = tmem_base + acc_cols + (uint32_t)(b * A_BUF_COLS);
+        const uint32_t lb_hi = desc_lo(sa + A_TILE_BYTES), lb_lo = desc_lo(sa + A_TILE_BYTES + b_tile_bytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 8; ++k4) {
+            if (k4 >= k_lo && k4 < k_hi) {
+              const uint32_t a_hi = a_hi0 + k4 * 8, a_lo = a_hi0 + 32 + k4 * 8;
+              const uint32_t acc = (ks > 0 || k4 > k_lo) ? 1u : 0u;
+              const uint32_t acc_m = (ks >= p.nacc || k4 > k_lo) ? 1u : 0u;
+              umma_tf32_ts_raw(d_lo, a_lo, desc_of(lb_hi + 2 * k4), idesc, acc);
+              umma_tf32_ts_raw(d_lo, a_hi, desc_of(lb_lo + 2 * k4), idesc, 1u);
+              umma_tf32_ts_raw(d_main, a_hi, desc_of(lb_hi + 2 * k4), idesc, acc_m);
+            }
+          }
+          umma_commit_raw(bar_empty + 8 * s);      // weights of stage s consumed by this stream
+          umma_commit_raw(bar_aempty + 8 * b);     // operand buffer b consumed by this stream
+        }
+        __syncwarp();
+      }
+      umma_commit(bar_tmem);
+    }
+  } else if (warp >= 2 && warp <= 5) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                  // GEMM row = TMEM lane = pixel within the tile
+    // ===== operand converter =====
+    for (int ks = 0; ks < nk; ++ks) {
+      const int s = ks % p.stages, b = ks & 1;
+      mbar_wait(bar_full + 8 * s, (uint32_t)(ks / p.stages) & 1u);
+      const uint8_t* row = smem_gen + (size_t)s * stage_bytes + (size_t)r * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {               // 16-byte chunk j of this row sits at chunk (j ^ (r & 7))
+        const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+        const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // hi = RN_tf32(a); lo = a - hi is exact in fp32 and |lo| <= 2^-12 |a|, so the tensor core's own
+          // truncation of lo to TF32 loses < 2^-23 |a|: no second rounding needed
+          uint32_t hb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a[k]));
+          hi[j * 4 + k] = hb; lo[j * 4 + k] = __float_as_uint(a[k] - __uint_as_float(hb));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);                        // this warp is done with the raw tile
+      mbar_wait(bar_aempty + 8 * b, ((uint32_t)(ks >> 1) & 1u) ^ 1u);        // MMAs that read buffer b have retired
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)(b * A_BUF_COLS);
+      tmem_st32(ta, hi);
+      tmem_st32(ta + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_afull + 8 * b);
+    }
+    // ===== epilogue =====
+    const int py = r / TW, px = r % TW;
+    const int iy = oy0 + py, ix = ox0 + px;
+    const bool valid = iy < p.Hy && ix < p.Wx;
+    const int oy = iy * p.out_stride + p.out_off_y, ox = ix * p.out_stride + p.out_off_x;
+    float* dst = p.y + ((((long long)n0 * p.Dout + z0) * p.Hout + oy) * p.Wout + ox) * (long long)p.Cs_out + p.c_off;
+    float* ep = reinterpret_cast<float*>(smem_gen);
+    const int EPS = BN + 1;
+    mbar_wait(bar_tmem, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool vec_ok = ((p.Cs_out | p.c_off) & 3) == 0;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float accv[16];
+      {
+        // accumulator order: cross-term accumulators first (small), then the main chains; fetched
+        // four at a time back to back with one wait
+        const int per = p.nacc + 1;                         // accumulators per issue stream: nacc mains + cross terms
+        const int used_m = nk < p.nacc ? nk : p.nacc;       // mains actually written (rotation per K-step)
+        const int n_acc = p.n_issue * (used_m + 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) accv[j] = 0.f;
+#pragma unroll 1
+        for (int a0 = 0; a0 < n_acc; a0 += 4) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (a0 + u < n_acc) {
+              const int idx = a0 + u;
+              // cross-term accumulators first (small), then the mains of every stream
+              const int slot = (idx < p.n_issue) ? idx * per + p.nacc : ((idx - p.n_issue) / used_m) * per + (idx - p.n_issue) % used_m;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0);
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                  : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]), "=r"(v[u][4]), "=r"(v[u][5]), "=r"(v[u][6]),
+                    "=r"(v[u][7]), "=r"(v[u][8]), "=r"(v[u][9]), "=r"(v[u][10]), "=r"(v[u][11]), "=r"(v[u][12]),
+                    "=r"(v[u][13]), "=r"(v[u][14]), "=r"(v[u][15])
+                  : "r"(taddr) : "memory");
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (a0 + u < n_acc) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(v[u][j]);
+            }
+        }
       }
       float f[16];
 #pragma unroll
@@ -244,8 +581,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
     }
     if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
-      const int e = threadIdx.x - 64;                        // 0..127
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
       for (int co = e; co < p.Cout; co += 128) {
         float s1 = 0.f, s2 = 0.f;
         for (int rr = 0; rr < 128; ++rr) { float x = ep[rr * EPS + co]; s1 += x; s2 = fmaf(x, x, s2); }
@@ -259,6 +596,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Development probe: raw tcgen05.mma issue / execution rate from resident shared-memory operands.
+// pattern 0: every MMA accumulates into the same columns; 1: destinations alternate over `nd`
+// accumulators per MMA; 2: groups of `grp` consecutive MMAs per destination. K slices cycle over the
+// four 32-byte slices of one 128-byte-swizzled tile. out[0] = cycles from first issue to completion.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+mma_probe_kernel(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_addr = smem_base, b_addr = smem_base + A_TILE_BYTES;
+  const uint32_t bar = smem_base + A_TILE_BYTES + 256 * 128;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + A_TILE_BYTES + 256 * 128 + 64);
+  const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
+  for (int i = threadIdx.x; i < (A_TILE_BYTES + 256 * 128) / 4; i += blockDim.x) reinterpret_cast<float*>(smem_gen)[i] = 1.0f;
+  if (threadIdx.x == 0) { mbar_init(bar, two_warps ? 2 : 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  long long t0 = 0;
+  if (warp == 1 || (two_warps && warp == 2)) {
+    const int w = warp == 1 ? 0 : 1;
+    t0 = clock64();
+    if (pattern == 3) {          // lean issue stream: one elect per 12 MMAs, immediate descriptor advance
+      const uint32_t la = desc_lo(a_addr), lb = desc_lo(b_addr);
+      const uint32_t d0 = tmem_base + (uint32_t)(w * nd * BN);
+      for (int i = 0; i < n_mma; i += 12) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j)
+            umma_tf32_raw(d0 + (uint32_t)((nd > 1 && (j % 3) != 2) ? BN : 0), desc_of(la + 2 * (j & 3)), desc_of(lb + 2 * (j & 3)), idesc, (i + j) >= 3 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+    } else
+    for (int i = 0; i < n_mma; ++i) {
+      int d;
+      if (pattern == 0) d = 0; else if (pattern == 1) d = i % nd; else d = (i / grp) % nd;
+      d += w * nd;
+      const uint64_t ad = umma_desc_sw128(a_addr + (i & 3) * 32);
+      const uint64_t bd = umma_desc_sw128(b_addr + (i & 3) * 32);
+      umma_tf32(tmem_base + (uint32_t)(d * BN), ad, bd, idesc, i >= nd ? 1u : 0u);
+    }
+    umma_commit(bar);
+    const long long t1 = clock64();
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    if (lane == 0 && w == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 // x -> hi = RN_tf32(x), lo = RN_tf32(x - hi)
@@ -300,7 +700,10 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int kind, int
   hi[i] = h; lo[i] = __uint_as_float(lb);
 }
 
-int g_force_nacc = 0;      // development knob (nrgbd_conv_tc_set_nacc): cap on the main accumulators
+int g_force_nacc = 0;
+int g_force_stages = 0;     // development knobs (nrgbd_conv_tc_set_dev)
+long long* g_dbg = nullptr;
+int g_dev_flags = 0;        // bit0: 1xTF32 (hi*hi only; v1: the lo tiles are not even loaded)      // development knob (nrgbd_conv_tc_set_nacc): cap on the main accumulators
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -353,17 +756,26 @@ int launch_tc(const float* x_hi, const float* x_lo, int N, int Din, int Hin, int
   if (rc != NRGBD_OK) return rc;
   p.cin_chunks = Cin_pad / BK;
   p.tiles_x = ceil_div(p.Wx, TW); p.tiles_y = ceil_div(p.Hy, TH);
-  int nacc = 512 / p.Cout_pad - 1;
-  if (nacc > 4) nacc = 4;
-  if (nacc < 1) nacc = 1;
-  if (g_force_nacc > 0 && g_force_nacc < nacc) nacc = g_force_nacc;
-  p.nacc = nacc;
-  int cols = 32; while (cols < (nacc + 1) * p.Cout_pad) cols <<= 1;
-  if (cols > 512) { nrgbd_set_error("conv_tc: accumulators do not fit TMEM"); return NRGBD_ERR_UNSUPPORTED; }
+  // Resource plan. The per-K-step time does not depend on the pipeline depth (measured), but a tile's
+  // prologue + epilogue are ~35 % of its lifetime: when Cout_pad <= 64 use 2 stages and 256 TMEM
+  // columns so that two CTAs share an SM and one's epilogue overlaps the other's main loop.
+  const bool two_per_sm = p.Cout_pad <= 64 && !(g_dev_flags & 2);
+  const int tmem_budget = two_per_sm ? 256 : 512;
+  // one lean issue stream reaches the hardware floor (tools/mma_probe.py: 48 cycles per N=64 MMA, the
+  // tensor floor for N >= 128), so the TMEM columns go to rotating main accumulators instead
+  int n_issue = ((g_dev_flags & 8) && 4 * p.Cout_pad <= tmem_budget) ? 2 : 1;
+  int nm = tmem_budget / (n_issue * p.Cout_pad) - 1;
+  if (nm > 4) nm = 4;
+  if (nm < 1) { nrgbd_set_error("conv_tc: accumulators do not fit TMEM"); return NRGBD_ERR_UNSUPPORTED; }
+  if (g_force_nacc > 0 && g_force_nacc < nm) nm = g_force_nacc;
+  p.n_issue = n_issue; p.nacc = nm; p.nl = 1;
+  int cols = 32; while (cols < n_issue * (nm + 1) * p.Cout_pad) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.Cout_pad * BK * 4;
-  int stages = (int)((220 * 1024 - 2048) / stage);
-  if (stages > 4) stages = 4;
+  int stages = two_per_sm ? 2 : (int)((220 * 1024 - 2048) / stage);
+  if (stages > 3) stages = 3;
+  if (g_force_stages > 0 && g_force_stages < stages) stages = g_force_stages;
+  p.dev_flags = g_dev_flags; p.dbg = g_dbg;
   if (stages < 2) { nrgbd_set_error("conv_tc: Cout too large for the shared-memory pipeline"); return NRGBD_ERR_UNSUPPORTED; }
   size_t ep_bytes = (size_t)128 * (p.Cout_pad + 1) * 4;
   p.stages = stages;
@@ -380,11 +792,66 @@ int launch_tc(const float* x_hi, const float* x_lo, int N, int Din, int Hin, int
   return NRGBD_OK;
 }
 
+// v2 launcher: raw activations, in-kernel split. Requires (nacc+1)*Cout_pad + 128 TMEM columns <= 512.
+int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi, const float* w_lo,
+               int n_wslices, TcParams& p, cudaStream_t st) {
+  CUtensorMap ta, tb_hi, tb_lo;
+  int rc = encode_act_map(&ta, x, N, Din, Hin, Win, Cin_pad, Cs_in, p.in_stride);
+  if (rc == NRGBD_OK) rc = encode_w_map(&tb_hi, w_hi, n_wslices, p.Cout_pad, Cin_pad);
+  if (rc == NRGBD_OK) rc = encode_w_map(&tb_lo, w_lo, n_wslices, p.Cout_pad, Cin_pad);
+  if (rc != NRGBD_OK) return rc;
+  p.cin_chunks = Cin_pad / BK;
+  p.tiles_x = ceil_div(p.Wx, TW); p.tiles_y = ceil_div(p.Hy, TH);
+  // Resource plan: Cout_pad <= 64 -> two CTAs per SM (one issue stream, 2 accumulators + 2 operand
+  // buffers = 256 TMEM columns, 3 x 32 KB stages); otherwise one CTA per SM.
+  const bool two_per_sm = p.Cout_pad <= 64 && !(g_dev_flags & 2);
+  const int tmem_budget = (two_per_sm ? 256 : 512) - 2 * A_BUF_COLS;
+  int n_issue = ((g_dev_flags & 8) && 4 * p.Cout_pad <= tmem_budget) ? 2 : 1;
+  int nm = tmem_budget / (n_issue * p.Cout_pad) - 1;
+  if (nm > 4) nm = 4;
+  if (nm < 1) { nrgbd_set_error("conv_tc2: Cout too large for the TMEM operand buffers"); return NRGBD_ERR_UNSUPPORTED; }
+  if (g_force_nacc > 0 && g_force_nacc < nm) nm = g_force_nacc;
+  p.n_issue = n_issue; p.nacc = nm; p.nl = 1;
+  int cols = 32; while (cols < n_issue * (nm + 1) * p.Cout_pad + 2 * A_BUF_COLS) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t stage = (size_t)A_TILE_BYTES + 2 * (size_t)p.Cout_pad * BK * 4;
+  int stages = two_per_sm ? 3 : (int)((220 * 1024 - 2048) / stage);
+  if (stages > 4) stages = 4;
+  if (g_force_stages > 0 && g_force_stages < stages) stages = g_force_stages;
+  p.dev_flags = g_dev_flags; p.dbg = nullptr;
+  if (stages < 2) { nrgbd_set_error("conv_tc2: Cout too large for the shared-memory pipeline"); return NRGBD_ERR_UNSUPPORTED; }
+  p.stages = stages;
+  size_t ep_bytes = (size_t)128 * (p.Cout_pad + 1) * 4;
+  size_t smem = (size_t)stages * stage + 1024 + 256;
+  if (stages * stage < ep_bytes) smem = ep_bytes + 1024 + 256;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { nrgbd_set_error("conv_tc2: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return NRGBD_ERR_CUDA; }
+    configured = smem;
+  }
+  const long long tiles = (long long)N * p.Dz * p.tiles_x * p.tiles_y;
+  conv_tc2_kernel<<<(unsigned)tiles, NUM_THREADS2, smem, st>>>(ta, tb_hi, tb_lo, p);
+  return NRGBD_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 void nrgbd_conv_tc_set_nacc(int n) { g_force_nacc = n; }
+void nrgbd_conv_tc_set_dev(int stages, int flags) { g_force_stages = stages; g_dev_flags = flags; }
+void nrgbd_conv_tc_set_debug_buffer(long long* buf) { g_dbg = buf; }
+
+// Development probe (see mma_probe_kernel). out: 2 int64 on the device (total cycles, issue cycles).
+int nrgbd_mma_probe(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, int n_ctas, long long* out, cudaStream_t st) {
+  NRGBD_REQUIRE(out && BN >= 16 && BN <= 256 && BN % 16 == 0 && nd >= 1 && (two_warps ? 2 : 1) * nd * BN <= 512 && grp >= 1, "bad arguments");
+  size_t smem = A_TILE_BYTES + 256 * 128 + 1024 + 256;
+  cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mma_probe_kernel<<<n_ctas, 128, smem, st>>>(BN, n_mma, pattern, nd, grp, two_warps, out);
+  NRGBD_LAUNCH_CHECK();
+  return NRGBD_OK;
+}
 
 // Whether the tensor-core path can run a convolution with these channel counts.
 int nrgbd_conv_tc_supported(int Cin_pad, int Cout_pad) {
@@ -470,6 +937,72 @@ int nrgbd_conv_transpose2d_k4s2_nhwc_tc(const float* x_hi, const float* x_lo, in
         }
       p.n_taps = 4;
       int rc = launch_tc(x_hi, x_lo, N, 1, Hin, Win, Cin_pad, Cs_in, w_hi, w_lo, 16, p, st);
+      if (rc != NRGBD_OK) return rc;
+    }
+  NRGBD_COUNT(4);
+  NRGBD_LAUNCH_CHECK();
+  return NRGBD_OK;
+}
+
+// v2 (in-kernel split): raw fp32 activations, TF32-split K-major weights. Cout_pad <= 128.
+int nrgbd_conv_tc2_supported(int Cin_pad, int Cout_pad) {
+  return (Cin_pad % 32 == 0 && Cin_pad >= 32 && Cout_pad % 16 == 0 && Cout_pad >= 16 && Cout_pad <= 128) ? 1 : 0;
+}
+
+int nrgbd_conv_nhwc_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
+                        const float* w_lo, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw, int stride, int pad,
+                        int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, cudaStream_t st) {
+  NRGBD_REQUIRE(x && w_hi && w_lo && y, "null pointer");
+  NRGBD_REQUIRE(nrgbd_conv_tc2_supported(Cin_pad, Cout_pad) && Cin_pad <= Cs_in && Cs_in % 4 == 0 && Cout <= Cout_pad,
+                "channel counts not supported by the tensor-core path");
+  NRGBD_REQUIRE(kd * kh * kw <= MAX_TAPS_TC && stride >= 1 && stride <= 8, "unsupported filter");
+  NRGBD_REQUIRE(Hout == (Hin + 2 * pad - dilation * (kh - 1) - 1) / stride + 1 &&
+                    Wout == (Win + 2 * pad - dilation * (kw - 1) - 1) / stride + 1, "output extent mismatch");
+  TcParams p;
+  p.y = y; p.bias = bias; p.stats = stats;
+  p.N = N; p.Dz = Din; p.Hy = Hout; p.Wx = Wout;
+  p.in_stride = stride; p.Cout = Cout; p.Cout_pad = Cout_pad;
+  p.Dout = Din; p.Hout = Hout; p.Wout = Wout; p.Cs_out = Cs_out; p.c_off = c_off;
+  p.out_stride = 1; p.out_off_y = 0; p.out_off_x = 0; p.leaky = leaky;
+  int t = 0;
+  for (int a = 0; a < kd; ++a)
+    for (int b = 0; b < kh; ++b)
+      for (int c = 0; c < kw; ++c) {
+        p.dz[t] = (signed char)(a - kd / 2); p.dy[t] = (signed char)(b * dilation - pad); p.dx[t] = (signed char)(c * dilation - pad);
+        p.wsel[t] = (unsigned char)t; ++t;
+      }
+  p.n_taps = t;
+  int rc = launch_tc2(x, N, Din, Hin, Win, Cin_pad, Cs_in, w_hi, w_lo, t, p, st);
+  if (rc != NRGBD_OK) return rc;
+  NRGBD_COUNT(1);
+  NRGBD_LAUNCH_CHECK();
+  return NRGBD_OK;
+}
+
+int nrgbd_conv_transpose2d_k4s2_nhwc_tc2(const float* x, int N, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
+                                         const float* w_lo, const float* bias, int Cout, int Cout_pad, float* y, int Cs_out,
+                                         int c_off, int leaky, cudaStream_t st) {
+  NRGBD_REQUIRE(x && w_hi && w_lo && y, "null pointer");
+  NRGBD_REQUIRE(nrgbd_conv_tc2_supported(Cin_pad, Cout_pad) && Cin_pad <= Cs_in && Cs_in % 4 == 0 && Cout <= Cout_pad,
+                "channel counts not supported by the tensor-core path");
+  const int kys[2][2] = {{1, 3}, {0, 2}};
+  const int dys[2][2] = {{0, -1}, {1, 0}};
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      TcParams p;
+      p.y = y; p.bias = bias; p.stats = nullptr;
+      p.N = N; p.Dz = 1; p.Hy = Hin; p.Wx = Win;
+      p.in_stride = 1; p.Cout = Cout; p.Cout_pad = Cout_pad;
+      p.Dout = 1; p.Hout = 2 * Hin; p.Wout = 2 * Win; p.Cs_out = Cs_out; p.c_off = c_off;
+      p.out_stride = 2; p.out_off_y = py; p.out_off_x = px; p.leaky = leaky;
+      int t = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          p.dz[t] = 0; p.dy[t] = (signed char)dys[py][a]; p.dx[t] = (signed char)dys[px][b];
+          p.wsel[t] = (unsigned char)(kys[py][a] * 4 + kys[px][b]); ++t;
+        }
+      p.n_taps = 4;
+      int rc = launch_tc2(x, N, 1, Hin, Win, Cin_pad, Cs_in, w_hi, w_lo, 16, p, st);
       if (rc != NRGBD_OK) return rc;
     }
   NRGBD_COUNT(4);

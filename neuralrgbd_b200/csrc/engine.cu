@@ -213,6 +213,13 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
   if (use_tc(e, x, Cout)) {
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, kd * k * k, false);
+    if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {       // in-kernel split, no extra pass
+      ProfScope ps(e, 0, flops);
+      ENG_CALL(e, nrgbd_conv_nhwc_tc2(x.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
+                                      stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
+                                      (nrgbd_stream_t)e->st));
+      return y;
+    }
     Act xh, xl;
     split_act(e, x, xh, xl);
     if (!e->rc) {
@@ -331,6 +338,12 @@ void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* 
   const double flops = 2.0 * 4.0 * (double)x.H * x.W * Cout * x.C * 4;
   if (use_tc(e, x, Cout)) {
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, 16, true);
+    if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {
+      ProfScope ps(e, 0, flops);
+      ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc_tc2(x.p, x.N, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, tb, Cout, pt->Cout_pad,
+                                                       dst.p, dst.Cs, 0, 1, st));
+      return;
+    }
     Act xh, xl;
     split_act(e, x, xh, xl);
     if (!e->rc) {

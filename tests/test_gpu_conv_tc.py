@@ -45,13 +45,14 @@ def test_split_tf32_is_exact_to_22_bits():
     dict(N=1, Cin=67, Cout=67, H=24, W=36, k=3, s=1, p=1, d=1),      # R-Net conv2 (padded to 96 / 80)
     dict(N=3, Cin=128, Cout=32, H=1, W=2, k=1, s=1, p=0, d=1),       # SPP branch on a 1x2 map
 ])
-def test_conv2d_tc_vs_oracle(cfg):
+@pytest.mark.parametrize('impl', ['v1', 'v2'])
+def test_conv2d_tc_vs_oracle(cfg, impl):
     from neuralrgbd_b200 import convops
     rng = np.random.RandomState(1)
     x = rng.standard_normal((cfg['N'], cfg['Cin'], cfg['H'], cfg['W'])).astype(np.float32)
     w = (rng.standard_normal((cfg['Cout'], cfg['Cin'], cfg['k'], cfg['k'])) / math.sqrt(cfg['Cin'] * cfg['k'] ** 2)).astype(np.float32)
     b = rng.standard_normal(cfg['Cout']).astype(np.float32)
-    y, st = convops.conv_tc(T(x), T(w), T(b), cfg['s'], cfg['p'], cfg['d'], leaky=True, want_stats=True)
+    y, st = convops.conv_tc(T(x), T(w), T(b), cfg['s'], cfg['p'], cfg['d'], leaky=True, want_stats=True, impl=impl)
     torch.cuda.synchronize()
     ref = N.leaky_relu(N.conv2d(x, w, b, cfg['s'], cfg['p'], cfg['d']))
     assert y.shape == ref.shape
@@ -65,25 +66,27 @@ def test_conv2d_tc_vs_oracle(cfg):
     assert np.abs(st[0] - got_sum).max() <= 1e-3 * max(1.0, np.abs(got_sum).max()) * 1e-2
 
 
-def test_conv3d_tc_vs_oracle():
+@pytest.mark.parametrize('impl', ['v1', 'v2'])
+def test_conv3d_tc_vs_oracle(impl):
     from neuralrgbd_b200 import convops
     rng = np.random.RandomState(2)
     for cin, cout in ((16, 64), (64, 64), (64, 1)):
         x = rng.standard_normal((1, cin, 9, 14, 18)).astype(np.float32)
         w = (rng.standard_normal((cout, cin, 3, 3, 3)) / math.sqrt(cin * 27)).astype(np.float32)
-        y = convops.conv_tc(T(x), T(w), None, 1, 1, 1)
+        y = convops.conv_tc(T(x), T(w), None, 1, 1, 1, impl=impl)
         ref = N.conv3d(x, w)
         assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
 
 
-def test_conv_transpose2d_tc_vs_oracle():
+@pytest.mark.parametrize('impl', ['v1', 'v2'])
+def test_conv_transpose2d_tc_vs_oracle(impl):
     from neuralrgbd_b200 import convops
     rng = np.random.RandomState(3)
     for cin, cout, h, w_ in ((128, 64, 9, 13), (96, 64, 16, 20)):
         x = rng.standard_normal((1, cin, h, w_)).astype(np.float32)
         w = (rng.standard_normal((cin, cout, 4, 4)) / math.sqrt(cin * 4)).astype(np.float32)
         b = rng.standard_normal(cout).astype(np.float32)
-        y = convops.conv_transpose2d_tc(T(x), T(w), T(b), leaky=True)
+        y = convops.conv_transpose2d_tc(T(x), T(w), T(b), leaky=True, impl=impl)
         ref = N.leaky_relu(N.conv_transpose2d(x, w, b, 2, 1))
         assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
 
@@ -97,3 +100,5 @@ def test_tc_matches_fp32_simt_path():
     a = convops.conv(T(x), T(w), None, 1, 1, 1).cpu().numpy()
     b = convops.conv_tc(T(x), T(w), None, 1, 1, 1).cpu().numpy()
     assert rel_err(b, a) <= 6e-6
+    c = convops.conv_tc(T(x), T(w), None, 1, 1, 1, impl='v2').cpu().numpy()
+    assert rel_err(c, a) <= 6e-6

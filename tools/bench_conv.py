@@ -49,7 +49,13 @@ def main():
     for a in sys.argv[1:]:
         if a.startswith('nacc='):
             L.nrgbd_conv_tc_set_nacc(int(a[5:]))
+        if a.startswith('dev='):
+            st_, fl_ = a[4:].split(',')
+            L.nrgbd_conv_tc_set_dev(int(st_), int(fl_))
+    only = [a[5:] for a in sys.argv[1:] if a.startswith('only=')]
     for name, N, D, H, W, Cin, Cout, k, s, p, d in SHAPES:
+        if only and not any(o in name for o in only):
+            continue
         kd = 3 if D > 1 else 1
         Cs = convops.pad_to(Cin, 32)
         x = torch.randn((N, D, H, W, Cs), device=dev)
@@ -74,10 +80,15 @@ def main():
         def tc():
             check(L.nrgbd_conv_nhwc_tc(ptr(xh), ptr(xl), N, D, H, W, Cs, Cs, ptr(wh), ptr(wl), None, Cout, convops.pad_to(Cout, 16), kd, k, k,
                                        s, p, d, ptr(y2), Ho, Wo, Cso, 0, 0, ctypes.c_void_p(stats.data_ptr()), st()))
-        t_simt = timeit(simt); t_split = timeit(split); t_tc = timeit(tc)
+        def tc2():
+            check(L.nrgbd_conv_nhwc_tc2(ptr(x), N, D, H, W, Cs, Cs, ptr(wh), ptr(wl), None, Cout, convops.pad_to(Cout, 16), kd, k, k,
+                                        s, p, d, ptr(y3), Ho, Wo, Cso, 0, 0, ctypes.c_void_p(stats.data_ptr()), st()))
+        y3 = torch.zeros_like(y)
+        t_simt = timeit(simt); t_split = timeit(split); t_tc = timeit(tc); t_tc2 = timeit(tc2)
         err = float((y - y2).abs().max() / y.abs().max())
         rec = dict(layer=name, gflop=flops / 1e9, simt_us=t_simt, simt_tflops=flops / t_simt / 1e6, split_us=t_split, tc_us=t_tc,
-                   tc_tflops=flops / t_tc / 1e6, tc_vs_simt_relerr=err)
+                   tc_tflops=flops / t_tc / 1e6, tc_vs_simt_relerr=err, tc2_us=t_tc2,
+                   tc2_tflops=flops / t_tc2 / 1e6, tc2_vs_simt_relerr=float((y - y3).abs().max() / y.abs().max()))
         out.append(rec)
         print(json.dumps(rec), flush=True)
     os.makedirs('gpurun_out', exist_ok=True)
