@@ -133,6 +133,10 @@ int nrgbd_conv_transpose2d_k4s2_nhwc(const float* x, int N, int Hin, int Win, in
 int nrgbd_bn_finalize(const double* stats, int C, double count, const float* gamma, const float* beta,
                       float eps, float* scale, float* shift, float* run_mean, float* run_var,
                       float momentum, nrgbd_stream_t stream);
+/* finalize + apply in one pass (C <= 512): scale/shift are derived per block from `stats`. */
+int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, const float* gamma, const float* beta,
+                         float eps, float* run_mean, float* run_var, float momentum, const float* res, int relu,
+                         long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);
 /* y = [relu](x*scale + shift) [+ res] over n_pos positions of Cs channels (C logical). */
 int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const float* res, int relu,
                    long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);

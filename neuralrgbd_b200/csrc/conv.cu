@@ -288,6 +288,52 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale, co
   reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// BatchNorm finalize + apply in one kernel: every block derives scale/shift for all C channels from
+// the accumulated statistics into shared memory (C <= 512), then streams its slice of the activation.
+// Block 0 also performs the training-mode running-statistics update.
+__global__ void __launch_bounds__(256)
+bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ stats, double count,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      float* __restrict__ run_mean, float* __restrict__ run_var, float momentum,
+                      const float* __restrict__ res, int relu, long long n4, int Cs, int C, float* __restrict__ y) {
+  __shared__ float s_scale[512], s_shift[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double mean = stats[c] / count;
+    double var = stats[C + c] / count - mean * mean;
+    if (var < 0) var = 0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = gamma[c] * invstd;
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - (float)mean * sc;
+    if (run_mean && blockIdx.x == 0) {
+      double unb = count > 1 ? var * count / (count - 1) : var;
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+    }
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)((i * 4) % Cs);
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c + k < C) {
+        float t = fmaf(o[k], s_scale[c + k], s_shift[c + k]);
+        if (relu) t = fmaxf(t, 0.f);
+        o[k] = t;
+      } else {
+        o[k] = 0.f;
+      }
+    }
+    if (res) {
+      float4 r = reinterpret_cast<const float4*>(res)[i];
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -399,6 +445,22 @@ int nrgbd_bn_finalize(const double* stats, int C, double count, const float* gam
   NRGBD_REQUIRE(stats && gamma && beta && scale && shift && C > 0 && count > 0, "bad arguments");
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(stats, C, count, gamma, beta, eps, scale, shift, run_mean,
                                                        run_var, momentum);
+  NRGBD_COUNT(1);
+  NRGBD_LAUNCH_CHECK();
+  return NRGBD_OK;
+}
+
+// Training-mode BatchNorm in one pass: finalize (scale/shift from the accumulated statistics, optional
+// running-stat update) + y = [relu](x*scale + shift) [+ res]. C <= 512.
+int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, const float* gamma, const float* beta, float eps,
+                         float* run_mean, float* run_var, float momentum, const float* res, int relu, long long n_pos, int Cs,
+                         int C, float* y, cudaStream_t st) {
+  NRGBD_REQUIRE(x && stats && gamma && beta && y && Cs % 4 == 0 && C <= Cs && C <= 512 && n_pos > 0 && count > 0, "bad arguments");
+  long long n4 = n_pos * Cs / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_apply_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
+                                                         n4, Cs, C, y);
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;

@@ -52,7 +52,9 @@ dpv_rows_strided_kernel(const float* __restrict__ a, const float* __restrict__ b
   if (conf) conf[pix] = cf;
 }
 
-// Contiguous variant: warp per pixel, D values consecutive in memory.
+// Contiguous variant: warp per pixel, D values consecutive in memory; each lane keeps its D/32 values
+// in registers (one read of the row, one write).
+template <int PER>      // values per lane: D <= 32 * PER
 __global__ void __launch_bounds__(256)
 dpv_rows_contig_kernel(const float* __restrict__ a, const float* __restrict__ b, float sign, int n_pix, int D,
                        float* __restrict__ y, long long ysd, long long ysp, const float* __restrict__ dpl,
@@ -62,25 +64,31 @@ dpv_rows_contig_kernel(const float* __restrict__ a, const float* __restrict__ b,
   if (pix >= n_pix) return;
   const float* pa = a + (long long)pix * D;
   const float* pb = b ? b + (long long)pix * D : nullptr;
+  float v[PER];
   float m = -INFINITY;
-  for (int d = lane; d < D; d += 32) {
-    float v = pa[d]; if (pb) v = __fadd_rn(v, pb[d]); v *= sign;
-    m = fmaxf(m, v);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int d = lane + 32 * k;
+    float t = -INFINITY;
+    if (d < D) { t = pa[d]; if (pb) t = __fadd_rn(t, pb[d]); t *= sign; }
+    v[k] = t;
+    m = fmaxf(m, t);
   }
   m = warp_max(m);
   float s = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float v = pa[d]; if (pb) v = __fadd_rn(v, pb[d]); v *= sign;
-    s += expf(v - m);
-  }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) if (lane + 32 * k < D) s += expf(v[k] - m);
   s = warp_sum(s);
   const float ls = logf(s);
   float dep = 0.f, cf = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float v = pa[d]; if (pb) v = __fadd_rn(v, pb[d]); v *= sign;
-    float o = (v - m) - ls;
-    if (y) y[(long long)d * ysd + (long long)pix * ysp] = o;
-    if (dpl) { float p = expf(o); dep += p * dpl[d]; cf = fmaxf(cf, p); }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int d = lane + 32 * k;
+    if (d < D) {
+      float o = (v[k] - m) - ls;
+      if (y) y[(long long)d * ysd + (long long)pix * ysp] = o;
+      if (dpl) { float p = expf(o); dep += p * dpl[d]; cf = fmaxf(cf, p); }
+    }
   }
   if (dpl) {
     dep = warp_sum(dep); cf = warp_max(cf);
@@ -126,9 +134,11 @@ int nrgbd_dpv_normalize(const float* a, long long in_sd, long long in_sp, const 
                         const float* d_planes, float* depth, float* conf, cudaStream_t st) {
   NRGBD_REQUIRE(a && n_pix > 0 && D > 0, "bad arguments");
   NRGBD_REQUIRE(out || (d_planes && (depth || conf)), "nothing to compute");
-  if (in_sd == 1 && in_sp == D && (!b || (b_sd == 1 && b_sp == D))) {
-    dpv_rows_contig_kernel<<<ceil_div((long long)n_pix * 32, 256), 256, 0, st>>>(a, b, sign, n_pix, D, out, out_sd,
-                                                                                out_sp, d_planes, depth, conf);
+  if (in_sd == 1 && in_sp == D && (!b || (b_sd == 1 && b_sp == D)) && D <= 256) {
+    const unsigned grid = (unsigned)ceil_div((long long)n_pix * 32, 256);
+    if (D <= 64) dpv_rows_contig_kernel<2><<<grid, 256, 0, st>>>(a, b, sign, n_pix, D, out, out_sd, out_sp, d_planes, depth, conf);
+    else if (D <= 128) dpv_rows_contig_kernel<4><<<grid, 256, 0, st>>>(a, b, sign, n_pix, D, out, out_sd, out_sp, d_planes, depth, conf);
+    else dpv_rows_contig_kernel<8><<<grid, 256, 0, st>>>(a, b, sign, n_pix, D, out, out_sd, out_sp, d_planes, depth, conf);
   } else {
     dpv_rows_strided_kernel<<<ceil_div(n_pix, 256), 256, 0, st>>>(a, b, sign, n_pix, D, in_sd, in_sp, b_sd, b_sp, out,
                                                                   out_sd, out_sp, d_planes, depth, conf);

@@ -251,10 +251,8 @@ Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k
   float* rm = e->bn_update_running ? param_opt(e, pre + ".1.running_mean") : nullptr;
   float* rv = e->bn_update_running ? param_opt(e, pre + ".1.running_var") : nullptr;
   if (e->rc) return y;
-  ENG_CALL(e, nrgbd_bn_finalize(e->stats, Cout, (double)y.pos(), g, b, 1e-5f, e->scale, e->shift, rm && rv ? rm : nullptr,
-                                rm && rv ? rv : nullptr, 0.1f, (nrgbd_stream_t)e->st));
-  ENG_CALL(e, nrgbd_bn_apply(y.p, e->scale, e->shift, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, y.p,
-                             (nrgbd_stream_t)e->st));
+  ENG_CALL(e, nrgbd_bn_apply_stats(y.p, e->stats, (double)y.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
+                                   0.1f, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, y.p, (nrgbd_stream_t)e->st));
   return y;
 }
 
@@ -269,9 +267,8 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
     float* rm = e->bn_update_running ? param_opt(e, pre + ".downsample.1.running_mean") : nullptr;
     float* rv = e->bn_update_running ? param_opt(e, pre + ".downsample.1.running_var") : nullptr;
     if (!e->rc) {
-      ENG_CALL(e, nrgbd_bn_finalize(e->stats, planes, (double)sc.pos(), g, b, 1e-5f, e->scale, e->shift,
-                                    rm && rv ? rm : nullptr, rm && rv ? rv : nullptr, 0.1f, (nrgbd_stream_t)e->st));
-      ENG_CALL(e, nrgbd_bn_apply(sc.p, e->scale, e->shift, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, (nrgbd_stream_t)e->st));
+      ENG_CALL(e, nrgbd_bn_apply_stats(sc.p, e->stats, (double)sc.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
+                                       0.1f, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, (nrgbd_stream_t)e->st));
     }
     res = &sc;
   }
@@ -306,22 +303,36 @@ void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
     ENG_CALL(e, nrgbd_copy_channels(raw.p, raw.pos(), raw.Cs, 0, 64, 0, cat.p, cat.Cs, 0, (nrgbd_stream_t)e->st));
     ENG_CALL(e, nrgbd_copy_channels(skip.p, skip.pos(), skip.Cs, 0, 128, 0, cat.p, cat.Cs, 64, (nrgbd_stream_t)e->st));
   }
-  // cat order (:161): raw, skip, branch4, branch3, branch2, branch1
+  // cat order (:161): raw, skip, branch4, branch3, branch2, branch1.
+  // SPP pooling (AvgPool2d 64/32/16/8, psm_submodule.py:103-117) is built hierarchically: the 8x8 means
+  // once from the feature map, then 16/32/64 as 2x2 means of the previous level (window origins are
+  // aligned multiples, so the result is the same mean; a 64x64 window pooled directly would run on
+  // N*1*2 blocks only).
   const int ks[4] = {64, 32, 16, 8};
   const int offs[4] = {288, 256, 224, 192};
-  for (int bi = 0; bi < 4 && !e->rc; ++bi) {
-    int k = ks[bi];
+  Act pools[4];
+  for (int bi = 3; bi >= 0 && !e->rc; --bi) {
+    const int k = ks[bi];
     if (skip.H / k < 1 || skip.W / k < 1) {
       nrgbd_set_error("engine: frame too small for the SPP AvgPool2d(%d) branch (need H/4, W/4 >= 64)", k);
       e->rc = NRGBD_ERR_BAD_ARG; break;
     }
-    Act pl = acquire(e, skip.N, 1, skip.H / k, skip.W / k, 128);
-    ENG_CALL(e, nrgbd_avgpool_nhwc(skip.p, skip.N, skip.H, skip.W, skip.Cs, 128, k, pl.p, pl.Cs, 0, (nrgbd_stream_t)e->st));
+    pools[bi] = acquire(e, skip.N, 1, skip.H / k, skip.W / k, 128);
+    if (bi == 3) {
+      ENG_CALL(e, nrgbd_avgpool_nhwc(skip.p, skip.N, skip.H, skip.W, skip.Cs, 128, 8, pools[bi].p, pools[bi].Cs, 0, (nrgbd_stream_t)e->st));
+    } else {
+      const Act& f = pools[bi + 1];
+      ENG_CALL(e, nrgbd_avgpool_nhwc(f.p, f.N, f.H, f.W, f.Cs, 128, 2, pools[bi].p, pools[bi].Cs, 0, (nrgbd_stream_t)e->st));
+    }
+  }
+  for (int bi = 0; bi < 4 && !e->rc; ++bi) {
+    Act& pl = pools[bi];
     Act br = convbn(e, pl, P + ".branch" + std::to_string(bi + 1) + ".1", 32, 1, 1, 1, 0, 1, true, nullptr);
     ENG_CALL(e, nrgbd_upsample_bilinear_ac_nhwc(br.p, br.N, br.H, br.W, br.Cs, 32, cat.p, cat.H, cat.W, cat.Cs, offs[bi],
                                                 (nrgbd_stream_t)e->st));
-    release(e, pl); release(e, br);
+    release(e, br);
   }
+  for (int bi = 0; bi < 4; ++bi) release(e, pools[bi]);
   release(e, raw); release(e, skip);
   Act lc = convbn(e, cat, P + ".lastconv.0", 128, 1, 3, 1, 1, 1, true, nullptr);
   release(e, cat);

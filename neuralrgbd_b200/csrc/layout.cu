@@ -25,6 +25,18 @@ __global__ void planes_to_interleaved_kernel(const float* __restrict__ in, int C
   }
 }
 
+// small C (<= 4): one thread per pixel, coalesced plane reads, one 16-byte store (Cs == 4, c_off == 0)
+__global__ void __launch_bounds__(256)
+planes_to_interleaved4_kernel(const float* __restrict__ in, int C, long long P, int N, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * N) return;
+  long long n = i / P, p = i - n * P;
+  const float* b = in + n * C * P + p;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) v[c] = b[(long long)c * P];
+  reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // in[p*Cs + c_off + c] -> out [C][P]
 __global__ void interleaved_to_planes_kernel(const float* __restrict__ in, int C, long long P, int Cs, int c_off,
                                              float* __restrict__ out) {
@@ -71,6 +83,29 @@ avgpool_nhwc_kernel(const float* __restrict__ x, int N, int H, int W, int Cs_in,
   }
 }
 
+// small windows (k <= 8): one thread per (output position, group of 4 channels), float4 loads
+__global__ void __launch_bounds__(256)
+avgpool_small_nhwc_kernel(const float* __restrict__ x, int N, int H, int W, int Cs_in, int C, int k, float* __restrict__ y,
+                          int Ho, int Wo, int Cs_out, int c_off) {
+  const int G = (C + 3) / 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * Ho * Wo * G) return;
+  int g = (int)(i % G); long long pos = i / G;
+  int ox = (int)(pos % Wo); int oy = (int)((pos / Wo) % Ho); int n = (int)(pos / ((long long)Wo * Ho));
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < k; ++r) {
+    const float* row = x + (((long long)n * H + oy * k + r) * W + (long long)ox * k) * Cs_in + g * 4;
+    for (int q = 0; q < k; ++q) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(row + (long long)q * Cs_in));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  const float inv = (float)(k * k);
+  float o[4] = {s.x / inv, s.y / inv, s.z / inv, s.w / inv};
+  float* dst = y + (((long long)n * Ho + oy) * Wo + ox) * Cs_out + c_off + g * 4;
+  for (int c = 0; c < 4; ++c) if (g * 4 + c < C) dst[c] = o[c];
+}
+
 __global__ void __launch_bounds__(256)
 upsample_bilinear_ac_kernel(const float* __restrict__ x, int N, int Hi, int Wi, int Cs_in, int C, float* __restrict__ y,
                             int Ho, int Wo, int Cs_out, int c_off, float sy, float sx) {
@@ -110,6 +145,12 @@ extern "C" {
 
 int nrgbd_nchw_to_nhwc(const float* x, int N, int C, long long P, float* y, int Cs, int c_off, cudaStream_t st) {
   NRGBD_REQUIRE(x && y && N > 0 && C > 0 && P > 0 && c_off + C <= Cs, "bad arguments");
+  if (C <= 4 && Cs == 4 && c_off == 0) {
+    planes_to_interleaved4_kernel<<<ceil_div(P * N, 256), 256, 0, st>>>(x, C, P, N, y);
+    NRGBD_COUNT(1);
+    NRGBD_LAUNCH_CHECK();
+    return NRGBD_OK;
+  }
   dim3 blk(32, 8), grid(ceil_div(P, 32), ceil_div(C, 32));
   for (int n = 0; n < N; ++n)
     planes_to_interleaved_kernel<<<grid, blk, 0, st>>>(x + (long long)n * C * P, C, P, Cs, c_off, y + (long long)n * P * Cs);
@@ -132,7 +173,12 @@ int nrgbd_avgpool_nhwc(const float* x, int N, int H, int W, int Cs_in, int C, in
                        cudaStream_t st) {
   NRGBD_REQUIRE(x && y && k >= 1 && H / k >= 1 && W / k >= 1 && C <= Cs_in && c_off + C <= Cs_out, "bad arguments");
   int Ho = H / k, Wo = W / k;
-  avgpool_nhwc_kernel<<<N * Ho * Wo, 256, 0, st>>>(x, N, H, W, Cs_in, C, k, y, Ho, Wo, Cs_out, c_off);
+  if (k <= 8 && Cs_in % 4 == 0) {
+    long long n = (long long)N * Ho * Wo * ((C + 3) / 4);
+    avgpool_small_nhwc_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, N, H, W, Cs_in, C, k, y, Ho, Wo, Cs_out, c_off);
+  } else {
+    avgpool_nhwc_kernel<<<N * Ho * Wo, 256, 0, st>>>(x, N, H, W, Cs_in, C, k, y, Ho, Wo, Cs_out, c_off);
+  }
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;

@@ -126,14 +126,17 @@ def build_model(c, cam):
     return m.to(dev)
 
 
+@pytest.mark.parametrize('conv_math', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('name', cases.KVNET_CASES)
-def test_kvnet_forward_streaming_vs_reference(golden, name):
+def test_kvnet_forward_streaming_vs_reference(golden, name, conv_math):
     """KVNET.forward first-window + steady branches and the streaming test() loop against the
     live-reference fixtures; each step is fed the REFERENCE's prior so deviations do not compound."""
     from neuralrgbd_b200.test_utils.test_KVNet import test as kv_test
     c = cases.kvnet_case(name)
     cam = cam_torch(cases.cam_for(O.make_cam_intrinsics, c['W'] // 4, c['H'] // 4))
-    model = torch.nn.DataParallel(build_model(c, cam), device_ids=[0])      # as test_KVNet.py:163
+    base = build_model(c, cam)
+    base.conv_math = conv_math        # exact fp32 CUDA-core path / tcgen05 3xTF32 tensor-core path: same gates
+    model = torch.nn.DataParallel(base, device_ids=[0])      # as test_KVNet.py:163
     n_steps = len(c['frames']) - 4
     bv_pred = None
     for step in range(n_steps):
@@ -181,11 +184,13 @@ def test_kvnet_forward_streaming_vs_reference(golden, name):
     assert torch.equal(a[3], b[3]) and torch.equal(a[0], b[0])
 
 
-def test_kvnet_vs_oracle_first_window():
+@pytest.mark.parametrize('conv_math', ['fp32', 'tf32x3'])
+def test_kvnet_vs_oracle_first_window(conv_math):
     """Engine vs the numpy oracle on a fresh seed (not in the fixtures)."""
     c = cases.kvnet_case('kvnet_256x320_d8')
     cam_np = cases.cam_for(O.make_cam_intrinsics, c['W'] // 4, c['H'] // 4)
     model = build_model(c, cam_torch(cam_np))
+    model.conv_math = conv_math
     ref_f, src_f, poses = cases.window(c, 3)
     with torch.no_grad():
         got = model(T(ref_f), T(src_f), T(poses), torch.zeros(1), cam_intrinsics=[cam_torch(cam_np)], BV_predict=None)
