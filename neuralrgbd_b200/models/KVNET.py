@@ -91,7 +91,7 @@ class KVNET(nn.Module):
         self.if_upsample_d = if_upsample_d
         self.cam_intrinsics = cam_intrinsics          # captured at construction: used by D-Net (KVNET.py:64-67)
         self.feat_dist = 'L2'                         # basic.py:146 default, never overridden by KVNET
-        self.conv_math = 'fp32'                       # 'fp32' (exact CUDA-core FFMA) | 'tf32x3' (tcgen05 tensor cores)
+        self.conv_math = 'tf32x3'                     # 'tf32x3' (tcgen05 tensor cores, error-compensated; default) | 'fp32' (exact CUDA-core FFMA)
 
         D = len(d_candi)
         gen = torch.Generator().manual_seed(0)
