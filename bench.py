@@ -29,6 +29,7 @@ import contextlib
 import ctypes
 import io
 import json
+import math
 import os
 import subprocess
 import sys
@@ -190,6 +191,7 @@ def run_engine(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('NRGBD_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     L = _lib.lib()
     peaks = read_peaks()
@@ -218,22 +220,38 @@ def run_engine(args):
     out_ref = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
     out_bv = torch.empty((D_PLANES, H_IMG // 4, W_IMG // 4), device=dev)
     out_dep = torch.empty((H_IMG // 4, W_IMG // 4), device=dev)
-    host_depth = torch.empty((1, H_IMG, W_IMG)).pin_memory()
-    host_conf = torch.empty((1, H_IMG, W_IMG)).pin_memory()
-    d2h_bytes = host_depth.numel() * 4 + host_conf.numel() * 4
+    d2h_bytes = 2 * H_IMG * W_IMG * 4
 
-    # one API-level call creates the engine, syncs weights and the camera
-    with torch.no_grad():
-        model(dev_frames[0][-1:], dev_frames[0][None, :-1], dev_poses[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
-    ent = model._engine(H_IMG, W_IMG, V_SRC, dev)
-    hnd = ent['h']
-    stream = torch.cuda.current_stream()
-    st = ctypes.c_void_p(stream.cuda_stream)
+    # one API-level call per engine creates it, syncs weights and the camera. `inflight` independent
+    # engines (own buffers, shared read-only weights) run consecutive frames on their own streams so that
+    # one frame's kernels fill the other's tail waves (750 conv tiles = 5.07 waves on 148 SMs).
+    inflight = max(1, args.inflight)
+    models = [model]
+    for _ in range(inflight - 1):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m2 = KVNET(64, cam, d, 10., 64, None, t_win_r=2)
+        m2.load_state_dict(model.state_dict())
+        m2 = m2.to(dev); m2.conv_math = args.conv_math
+        models.append(m2)
+    streams = [torch.cuda.current_stream()] + [torch.cuda.Stream(device=dev) for _ in range(inflight - 1)]
+    hnds = []
+    for m_, s_ in zip(models, streams):
+        with torch.cuda.stream(s_), torch.no_grad():
+            m_(dev_frames[0][-1:], dev_frames[0][None, :-1], dev_poses[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+        hnds.append(m_._engine(H_IMG, W_IMG, V_SRC, dev)['h'])
+    torch.cuda.synchronize()
+    hnd = hnds[0]
+    stream = streams[0]
+    outs = [(torch.empty_like(out_ref), torch.empty_like(out_bv), torch.empty_like(out_dep)) for _ in range(inflight)]
 
     def step_resident(i):
-        flush.zero_()
-        check(L.nrgbd_kvnet_forward(hnd, ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(out_ref), None,
-                                    ptr(out_bv), None, ptr(out_dep), None, st))
+        k = i % inflight
+        sk = streams[k]
+        with torch.cuda.stream(sk):
+            if k == 0:
+                flush.zero_()
+            check(L.nrgbd_kvnet_forward(hnds[k], ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(outs[k][0]), None,
+                                        ptr(outs[k][1]), None, ptr(outs[k][2]), None, ctypes.c_void_p(sk.cuda_stream)))
 
     def barrier():
         if world > 1:
@@ -241,12 +259,14 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     # ---------------- value: inputs resident in HBM ----------------
+    # untimed priming: every (engine, window) pointer tuple gets its CUDA graph captured before any timing
+    n_prime = inflight * n_win // math.gcd(inflight, n_win)
+    for i in range(n_prime):
+        step_resident(i)
+    torch.cuda.synchronize()
     for i in range(Wm):
         step_resident(i)
-    check(L.nrgbd_kvnet_set_option(hnd, b'profile', 1))
     ms_c, wk_c, n_c = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-    L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))   # clear
-    L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -254,12 +274,32 @@ def run_engine(args):
     L.nrgbd_reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    for s_ in streams[1:]:
+        s_.wait_stream(stream)
     for i in range(K):
         step_resident(Wm + i)
+    for s_ in streams[1:]:
+        stream.wait_stream(s_)
     e1.record(stream)
     barrier()
     launches = int(L.nrgbd_launch_count())
     ms_total = e0.elapsed_time(e1)
+    # per-kernel CUDA-event profile: the timed steps are CUDA-graph replays (one launch per frame), which cannot
+    # carry per-kernel events, so the same step is run P_PROF more times eagerly, back to back on the same
+    # stream right after the timed region, with the engine's event brackets around its conv / sweep launches
+    P_PROF = 4
+    check(L.nrgbd_kvnet_set_option(hnd, b'profile', 1))
+    L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))   # clear
+    L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for i in range(P_PROF):
+        flush.zero_()
+        check(L.nrgbd_kvnet_forward(hnd, ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(outs[0][0]), None,
+                                    ptr(outs[0][1]), None, ptr(outs[0][2]), None, ctypes.c_void_p(stream.cuda_stream)))
+    p1.record(stream)
+    torch.cuda.synchronize()
+    prof_ms_total = p0.elapsed_time(p1)
     check(L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
     conv_ms, conv_flops, conv_n = ms_c.value, wk_c.value, n_c.value
     check(L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
@@ -272,22 +312,49 @@ def run_engine(args):
     value = world * K / (ms_max * 1e-3)
 
     # ---------------- e2e: public Python surface, pinned host buffers ----------------
+    # The same pipelining a video application uses: `inflight` model instances, each on its own stream
+    # with its own pinned staging buffers. Every step still does its H2D of the 5-frame window + poses, the
+    # forward through KVNET.forward + depth regression, and the D2H of the full-resolution depth and
+    # confidence maps; the host consumes a step's result when that stream is next reused (or at the end).
+    h_depth = [torch.empty((1, H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
+    h_conf = [torch.empty((1, H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
+    done_ev = [None] * inflight
+    consumed = [0]
+
+    def consume(k):
+        if done_ev[k] is not None:
+            done_ev[k].synchronize()              # the user reads the depth map on the host
+            consumed[0] += float(h_depth[k][0, 0, 0]) * 0.0 + 1
+
     def step_e2e(i):
-        flush.zero_()
-        f = pin_frames[i % n_win].to(dev, non_blocking=True)
-        p = pin_poses[i % n_win].to(dev, non_blocking=True)
-        with torch.no_grad():
-            out = model(f[-1:], f[None, :-1], p[None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
-            dep, conf = misc.depth_val_regression(out[0], d, BV_log=True, return_conf=True)
-        host_depth.copy_(dep, non_blocking=True)
-        host_conf.copy_(conf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the user reads the depth map on the host
-    for i in range(Wm):
+        k = i % inflight
+        consume(k)
+        sk = streams[k]
+        with torch.cuda.stream(sk):
+            if k == 0:
+                flush.zero_()
+            f = pin_frames[i % n_win].to(dev, non_blocking=True)
+            p = pin_poses[i % n_win].to(dev, non_blocking=True)
+            with torch.no_grad():
+                out = models[k](f[-1:], f[None, :-1], p[None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+                dep, conf = misc.depth_val_regression(out[0], d, BV_log=True, return_conf=True)
+            h_depth[k].copy_(dep, non_blocking=True)
+            h_conf[k].copy_(conf, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(sk); done_ev[k] = ev
+    for i in range(n_prime + Wm):          # priming (graph capture per pointer tuple) + warm-up, untimed
         step_e2e(i)
+    for k in range(inflight):
+        consume(k); done_ev[k] = None
     barrier()
     e0.record(stream)
+    for s_ in streams[1:]:
+        s_.wait_stream(stream)
     for i in range(K):
         step_e2e(Wm + i)
+    for k in range(inflight):
+        consume(k)
+    for s_ in streams[1:]:
+        stream.wait_stream(s_)
     e1.record(stream)
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -295,6 +362,7 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * K / (float(t.item()) * 1e-3)
     sampler.stop = True
+    host_depth = h_depth[0]
     assert np.isfinite(host_depth.numpy()).all()
 
     if rank == 0:
@@ -306,16 +374,18 @@ def run_engine(args):
             'steps': K, 'warmup': Wm, 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32' if args.conv_math == 'fp32' else 'f32 (3xTF32 error-compensated tensor-core products, fp32 accumulate)', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'conv_math': args.conv_math, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG], 'parallelism': 'dp%d (frames sharded, weights NCCL-broadcast once)' % world,
-                       'l2': 'explicit 256 MiB flush write before every step (inside the timed region)',
+                       'l2': 'explicit 256 MiB flush write before every %s step (inside the timed region)' % ('second' if inflight == 2 else '%d-th' % inflight if inflight > 2 else ''),
+                       'frames_in_flight': inflight,
                        'weights': 'random init of the reference architecture (arch.synth_state_dict seed 5)',
                        'sweep': {'avg_us': 1e3 * sw_ms / max(sw_n, 1), 'algorithmic_GBps': sweep_gbs, 'frac_of_hbm_peak': sweep_gbs / peaks['hbm_gbs'],
                                  'note': 'fused plane-sweep cost kernel incl. setup launch; C=67 is L1/FFMA bound, not HBM bound (SURVEY 8d)'},
-                       'conv_share_of_step': conv_ms / ms_total if ms_total > 0 else None},
+                       'conv_share_of_step': conv_ms / prof_ms_total if prof_ms_total > 0 else None,
+                       'cuda_graph': 'each frame is one cudaGraphLaunch (captured per I/O pointer tuple after an eager warm-up)'},
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
             'gpu_launches': launches,
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': conv_tflops, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': conv_tflops / peak_tf,
-                         'traffic': None, 'kernel': ('conv_tc_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)' if args.conv_math == 'tf32x3' else 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)') + ', %d launches/step, avg %.1f us' % (conv_n // max(K, 1), 1e3 * conv_ms / max(conv_n, 1)),
+                         'traffic': None, 'kernel': ('conv_tc2_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)' if args.conv_math == 'tf32x3' else 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)') + ', %d launches/step, avg %.1f us (CUDA events around every conv launch in %d eager frames run right after the timed graph replays)' % (conv_n // P_PROF, 1e3 * conv_ms / max(conv_n, 1), P_PROF),
                          'peak_source': peaks['source'] + ', sustained bf16'},
         }
         # cpu baseline: bounded sample of the same workload through the oracle port (rank 0, N = 1 only)
@@ -337,6 +407,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight on separate streams (resident-value loop)')
     ap.add_argument('--conv-math', default='tf32x3', choices=['fp32', 'tf32x3'],
                     help='fp32: exact CUDA-core FFMA implicit GEMM; tf32x3: tcgen05 error-compensated 3xTF32 (default)')
     args = ap.parse_args()

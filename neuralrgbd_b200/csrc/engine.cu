@@ -92,6 +92,19 @@ struct nrgbd_kvnet {
   float* conf = nullptr;
   // optional per-kernel event profiling (bench.py roofline): category 0 = conv (work = flops),
   // 1 = plane sweep (work = algorithmic bytes)
+  // CUDA-graph replay of a whole frame: after one eager (warm-up) forward every buffer the frame needs is in
+  // the pool and every weight is packed, so the launch sequence is static; it is captured once per distinct
+  // tuple of caller pointers and replayed (≈330 launches + ≈90 memsets become one cudaGraphLaunch).
+  int use_graph = 1;
+  bool warm = false;            // eager first-window forward done
+  bool warm_steady = false;     // eager K-Net (steady-state) forward done
+  struct GraphEnt { int variant; cudaStream_t stream; cudaGraphExec_t exec; long long launches; };
+  float* x0_buf = nullptr;          // [V+1][H][W][4] input frames, channels-last
+  float* rt_buf = nullptr;          // [V][3][3] rotations then [V][3] translations
+  float* ref_cur_hwd = nullptr;     // [HW][D] refined log-DPV of the measurement
+  float* ref_kv_hwd = nullptr;      // [HW][D] refined log-DPV of the filtered DPV (steady state)
+  std::vector<GraphEnt> graphs;
+  unsigned long long graph_clock = 0;
   int profile = 0;
   struct ProfRec { cudaEvent_t a, b; int cat; double work; };
   std::vector<ProfRec> prof;
@@ -372,7 +385,7 @@ void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* 
 }
 
 // models/Refine.py:79-107. prob source: log-DPV pixel-major [hw][D]; returns log-DPV [H*W][D].
-Act r_net(Eng* e, const float* bv_hwd, const float* feat_ref, int feat_Cs, const float* l1_ref, int l1_Cs, const Act& frame_ref) {
+void r_net(Eng* e, const float* bv_hwd, const float* feat_ref, int feat_Cs, const float* l1_ref, int l1_Cs, const Act& frame_ref, Act& out) {
   const int D = e->D, h = e->h, w = e->w, H = e->H, W = e->W, F = e->F;
   const long long hw = (long long)h * w;
   nrgbd_stream_t st = (nrgbd_stream_t)e->st;
@@ -395,11 +408,10 @@ Act r_net(Eng* e, const float* bv_hwd, const float* feat_ref, int feat_Cs, const
   release(e, d);
   Act f = conv(e, t1, "r_net.conv2.0.weight", D + 3, 1, 3, 1, 1, 1, "r_net.conv2.0.bias", true, false); release(e, t1);
   Act g = conv(e, f, "r_net.conv2_1.0.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_1.0.bias", true, false); release(e, f);
-  Act o = conv(e, g, "r_net.conv2_2.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_2.bias", false, false, nullptr, 0, D); release(e, g);
+  conv(e, g, "r_net.conv2_2.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_2.bias", false, false, &out, 0, D); release(e, g);
   // F.log_softmax(conv2_2_out, dim=1): channels are contiguous per pixel (Cs == D)
   if (!e->rc)
-    ENG_CALL(e, nrgbd_dpv_normalize(o.p, 1, D, nullptr, 0, 0, 1.f, H * W, D, o.p, 1, D, nullptr, nullptr, nullptr, st));
-  return o;
+    ENG_CALL(e, nrgbd_dpv_normalize(out.p, 1, D, nullptr, 0, 0, 1.f, H * W, D, out.p, 1, D, nullptr, nullptr, nullptr, st));
 }
 
 // models/basic.py:113-139 on a channels-last volume [D][h][w][CK] -> gain [D][hw] (DHW, Cs = 1)
@@ -421,6 +433,19 @@ Act kv_net(Eng* e, const Act& vol) {
   Act gain = conv(e, o, "kv_net.classify.2.weight", 1, 3, 3, 1, 1, 1, nullptr, false, false, nullptr, 0, 1);
   release(e, o);
   return gain;
+}
+
+// rt[v*9 + i*3 + j] = pose_v[i][j]; rt[9V + v*3 + i] = pose_v[i][3]
+__global__ void gather_rt_kernel(const float* __restrict__ poses, int V, float* __restrict__ rt) {
+  int i = threadIdx.x;
+  if (i < 9 * V) { int v = i / 9, r = (i % 9) / 3, c = i % 3; rt[i] = poses[v * 16 + r * 4 + c]; }
+  else if (i < 12 * V) { int k = i - 9 * V, v = k / 3, r = k % 3; rt[i] = poses[v * 16 + r * 4 + 3]; }
+}
+
+void drop_graphs(Eng* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+  e->warm = false; e->warm_steady = false;
 }
 
 int upload(float** dst, const float* host, size_t n) {
@@ -468,6 +493,8 @@ int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
   for (int i = 0; i < 2; ++i) { cudaFree(e->cam[i].K); cudaFree(e->cam[i].rays); }
   cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
   cudaFree(e->bv_cur_hwd); cudaFree(e->dpv_hwd); cudaFree(e->prior_hwd); cudaFree(e->depth); cudaFree(e->conf);
+  cudaFree(e->x0_buf); cudaFree(e->rt_buf); cudaFree(e->ref_cur_hwd); cudaFree(e->ref_kv_hwd);
+  drop_graphs(e);
   e->pool.destroy();
   for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->ev_free) cudaEventDestroy(ev);
@@ -480,6 +507,7 @@ int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
 // Setting a conv weight again invalidates its packed copy.
 int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, long long n, int is_device) {
   NRGBD_REQUIRE(e && name && data && n > 0, "bad arguments");
+  drop_graphs(e);
   std::string key(name);
   if (key.rfind("module.", 0) == 0) key = key.substr(7);                         // DataParallel prefix
   const std::string alias = "d_net.feature_extraction.";                          // same tensors, second name (KVNET.py:63-67)
@@ -513,6 +541,7 @@ int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, l
 int nrgbd_kvnet_set_camera(nrgbd_kvnet* e, int slot, const float* K_host, const float* rays_host, float cx, float cy,
                            double hfov_deg, double vfov_deg) {
   NRGBD_REQUIRE(e && (slot == 0 || slot == 1) && K_host && rays_host, "bad arguments");
+  drop_graphs(e);
   Camera& c = e->cam[slot];
   int rc = upload(&c.K, K_host, 9);
   if (rc == NRGBD_OK) rc = upload(&c.rays, rays_host, (size_t)3 * e->h * e->w);
@@ -526,6 +555,7 @@ int nrgbd_kvnet_set_camera(nrgbd_kvnet* e, int slot, const float* K_host, const 
 
 int nrgbd_kvnet_set_planes(nrgbd_kvnet* e, const float* d_host, int D) {
   NRGBD_REQUIRE(e && d_host && D == e->D, "d_candi length must equal the engine's D");
+  drop_graphs(e);
   e->d_host.assign(d_host, d_host + D);
   int rc = upload(&e->d_planes, d_host, D);
   if (rc != NRGBD_OK) nrgbd_set_error("nrgbd_kvnet_set_planes: upload failed");
@@ -535,11 +565,12 @@ int nrgbd_kvnet_set_planes(nrgbd_kvnet* e, const float* d_host, int D) {
 int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value) {
   NRGBD_REQUIRE(e && key, "bad arguments");
   std::string k(key);
-  if (k == "bn_update_running") { e->bn_update_running = value; return NRGBD_OK; }
+  if (k == "bn_update_running") { drop_graphs(e); e->bn_update_running = value; return NRGBD_OK; }
   if (k == "profile") { e->profile = value; return NRGBD_OK; }
+  if (k == "use_graph") { drop_graphs(e); e->use_graph = value; return NRGBD_OK; }
   if (k == "conv_math") {            // 0: exact fp32 (CUDA cores); 1: tcgen05 3xTF32 (tensor cores)
     if (value != 0 && value != 1) { nrgbd_set_error("conv_math must be 0 (fp32) or 1 (tf32x3)"); return NRGBD_ERR_BAD_ARG; }
-    e->conv_math = value; return NRGBD_OK;
+    drop_graphs(e); e->conv_math = value; return NRGBD_OK;
   }
   nrgbd_set_error("nrgbd_kvnet_set_option: unknown option '%s'", key);
   return NRGBD_ERR_BAD_ARG;
@@ -573,38 +604,126 @@ int nrgbd_kvnet_profile_read(nrgbd_kvnet* e, int category, double* ms, double* w
 //  :142 reads one element on the host and is done by the caller.)
 //  outputs (device, any may be NULL): dmap_cur_refined [D][H][W], dmap_refined [D][H][W],
 //  bv_cur [D][h][w], dpv [D][h][w]; depth_lowres/conf_lowres [h][w] = expected depth / max prob of dpv.
+// ---- one depth frame = eager head -> core (CUDA graph) -> eager tail --------------------------------
+// head: caller inputs -> engine-owned buffers (frames to channels-last, R|t gather, prior to pixel-major)
+// core: D-Net, R-Net, [K-Net, R-Net] entirely on engine-owned memory (graph-captured per branch/need-set)
+// tail: engine results -> caller tensors in the reference layouts ([D][H][W] / [D][h][w])
+static int ensure_io_buffers(nrgbd_kvnet* e) {
+  if (e->x0_buf) return NRGBD_OK;
+  const size_t HW = (size_t)e->H * e->W;
+  bool ok = cudaMalloc((void**)&e->x0_buf, sizeof(float) * (e->V + 1) * HW * 4) == cudaSuccess &&
+            cudaMalloc((void**)&e->rt_buf, sizeof(float) * 12 * e->V) == cudaSuccess &&
+            cudaMalloc((void**)&e->ref_cur_hwd, sizeof(float) * HW * e->D) == cudaSuccess &&
+            cudaMalloc((void**)&e->ref_kv_hwd, sizeof(float) * HW * e->D) == cudaSuccess;
+  if (!ok) { nrgbd_set_error("engine: cudaMalloc failed for the I/O staging buffers"); return NRGBD_ERR_NOMEM; }
+  cudaMemset(e->x0_buf, 0, sizeof(float) * (e->V + 1) * HW * 4);      // pad channel stays 0
+  return NRGBD_OK;
+}
+
+static int forward_head(nrgbd_kvnet* e, const float* frames, const float* poses, const float* bv_predict, nrgbd_stream_t st) {
+  const int V = e->V, N = V + 1;
+  const long long HW = (long long)e->H * e->W, hw = (long long)e->h * e->w;
+  int rc = nrgbd_nchw_to_nhwc(frames, N, 3, HW, e->x0_buf, 4, 0, st);
+  if (rc) return rc;
+  // Rs / ts (basic.py:266-267): gather 3x3 and 3 from the V 4x4 poses
+  gather_rt_kernel<<<1, 32 * ((12 * V + 31) / 32), 0, (cudaStream_t)st>>>(poses, V, e->rt_buf);
+  nrgbd_count_launch(1);
+  if (bv_predict) { rc = nrgbd_transpose2d(bv_predict, e->D, (int)hw, e->prior_hwd, st); if (rc) return rc; }
+  return NRGBD_OK;
+}
+
+static int forward_core(nrgbd_kvnet* e, bool steady, bool need_cur_refined, bool need_kv_refined, nrgbd_stream_t stream);
+
+static int forward_tail(nrgbd_kvnet* e, bool steady, float* dmap_cur_refined, float* dmap_refined, float* bv_cur, float* dpv,
+                        float* depth_lowres, float* conf_lowres, nrgbd_stream_t st) {
+  const int D = e->D;
+  const long long HW = (long long)e->H * e->W, hw = (long long)e->h * e->w;
+  int rc = NRGBD_OK;
+  if (bv_cur && !rc) rc = nrgbd_transpose2d(e->bv_cur_hwd, (int)hw, D, bv_cur, st);
+  if (dpv && !rc) rc = nrgbd_transpose2d(e->dpv_hwd, (int)hw, D, dpv, st);
+  if (dmap_cur_refined && !rc) rc = nrgbd_transpose2d(e->ref_cur_hwd, (int)HW, D, dmap_cur_refined, st);
+  if (dmap_refined && !rc) rc = nrgbd_transpose2d(steady ? e->ref_kv_hwd : e->ref_cur_hwd, (int)HW, D, dmap_refined, st);
+  if (rc) return rc;
+  if (depth_lowres) NRGBD_CUDA_CHECK(cudaMemcpyAsync(depth_lowres, e->depth, sizeof(float) * hw, cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+  if (conf_lowres) NRGBD_CUDA_CHECK(cudaMemcpyAsync(conf_lowres, e->conf, sizeof(float) * hw, cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+  return NRGBD_OK;
+}
+
 int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses, const float* bv_predict,
                         float* dmap_cur_refined, float* dmap_refined, float* bv_cur, float* dpv, float* depth_lowres,
                         float* conf_lowres, nrgbd_stream_t stream) {
   NRGBD_REQUIRE(e && frames && poses, "null input");
   NRGBD_REQUIRE(e->cam[0].set && e->d_planes, "camera / depth planes not set");
   NRGBD_REQUIRE(!bv_predict || e->cam[1].set, "per-call camera (slot 1) not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_io_buffers(e);
+  if (rc) return rc;
+  const bool steady = bv_predict != nullptr;
+  const bool need_cur = dmap_cur_refined != nullptr || (!steady && dmap_refined != nullptr);
+  const bool need_kv = steady && dmap_refined != nullptr;
+  rc = forward_head(e, frames, poses, bv_predict, stream);
+  if (rc) return rc;
+
+  const int variant = (steady ? 4 : 0) | (need_cur ? 2 : 0) | (need_kv ? 1 : 0);
+  const bool branch_warm = steady ? e->warm_steady : e->warm;
+  bool done = false;
+  if (e->use_graph && branch_warm && !e->profile) {
+    for (auto& g : e->graphs) {
+      if (g.variant == variant && g.stream == st) {
+        NRGBD_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+        nrgbd_count_launch((int)g.launches);
+        done = true;
+        break;
+      }
+    }
+    if (!done) {
+      // capture the core for this (branch, needed outputs, stream): same kernels in the same order - the buffer
+      // pool is deterministic after the eager warm-up of the branch
+      const long long before = nrgbd_launch_count();
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        int crc = forward_core(e, steady, need_cur, need_kv, stream);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        const long long captured = nrgbd_launch_count() - before;
+        cudaGraphExec_t exec = nullptr;
+        if (crc == NRGBD_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess && exec) {
+          nrgbd_kvnet::GraphEnt g; g.variant = variant; g.stream = st; g.exec = exec; g.launches = captured;
+          e->graphs.push_back(g);
+          NRGBD_CUDA_CHECK(cudaGraphLaunch(exec, st));        // the captured work has not run yet
+          done = true;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (crc != NRGBD_OK) return crc;
+      }
+      cudaGetLastError();
+    }
+  }
+  if (!done) {
+    rc = forward_core(e, steady, need_cur, need_kv, stream);
+    if (rc) return rc;
+    if (steady) e->warm_steady = true; else e->warm = true;
+  }
+  return forward_tail(e, steady, dmap_cur_refined, dmap_refined, bv_cur, dpv, depth_lowres, conf_lowres, stream);
+}
+
+// One depth frame on engine-owned memory (models/KVNET.py:93-185, if_refined=True, refineNet_name='DPV').
+// Inputs: x0_buf (frames, channels-last, sources then reference), rt_buf (R|t), prior_hwd (steady only).
+// Results: bv_cur_hwd, dpv_hwd, depth, conf, ref_cur_hwd / ref_kv_hwd (log-DPVs at image size, pixel-major).
+static int forward_core(nrgbd_kvnet* e, bool steady, bool need_cur_refined, bool need_kv_refined, nrgbd_stream_t stream) {
   e->st = (cudaStream_t)stream; e->rc = 0;
   nrgbd_stream_t st = stream;
   const int H = e->H, W = e->W, D = e->D, V = e->V, h = e->h, w = e->w, F = e->F, N = V + 1;
   const long long hw = (long long)h * w, HW = (long long)H * W;
 
   // ---- D-Net: features for the V+1 frames as one batch (basic.py:244-252) ------------------------
-  Act x0 = acquire(e, N, 1, H, W, 3);
-  ENG_CALL(e, nrgbd_nchw_to_nhwc(frames, N, 3, HW, x0.p, x0.Cs, 0, st));
+  Act x0; x0.p = e->x0_buf; x0.N = N; x0.D = 1; x0.H = H; x0.W = W; x0.C = 3; x0.Cs = 4;
   Act l1, feat;
   feature_cnn(e, x0, l1, feat);
   // image intensity features: avg_pool2d(rgb, 4) (basic.py:254-263) -> the sweep's narrow layout [N][hw][4]
   Act rgbq = acquire(e, N, 1, h, w, 3);
   ENG_CALL(e, nrgbd_avgpool_nhwc(x0.p, N, H, W, x0.Cs, 3, 4, rgbq.p, rgbq.Cs, 0, st));
-  // Rs / ts (basic.py:266-267): gather 3x3 and 3 from the 4x4 poses
-  float* Rt = e->pool.acquire(sizeof(float) * 12 * V);
-  if (!Rt && !e->rc) { e->rc = NRGBD_ERR_NOMEM; nrgbd_set_error("engine: out of memory"); }
-  if (!e->rc) {
-    for (int v = 0; v < V; ++v) {
-      cudaMemcpy2DAsync(Rt + v * 9, 3 * sizeof(float), poses + v * 16, 4 * sizeof(float), 3 * sizeof(float), 3,
-                        cudaMemcpyDeviceToDevice, e->st);
-      cudaMemcpy2DAsync(Rt + 9 * V + v * 3, sizeof(float), poses + v * 16 + 3, 4 * sizeof(float), sizeof(float), 3,
-                        cudaMemcpyDeviceToDevice, e->st);
-    }
-  }
-  const float* Rs = Rt; const float* ts = Rt ? Rt + 9 * V : nullptr;
-  const size_t featS = (size_t)hw * pad4(F);
+  const float* Rs = e->rt_buf; const float* ts = e->rt_buf + 9 * V;
+  const size_t featS = (size_t)hw * feat.Cs;
   const Camera& c0 = e->cam[0];
   if (!e->rc) {
     {
@@ -617,28 +736,20 @@ int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses,
     ENG_CALL(e, nrgbd_dpv_normalize(e->dpv_hwd, 1, D, nullptr, 0, 0, -1.f, (int)hw, D, e->bv_cur_hwd, 1, D, e->d_planes,
                                     e->depth, e->conf, st));
   }
-  if (bv_cur) ENG_CALL(e, nrgbd_transpose2d(e->bv_cur_hwd, (int)hw, D, bv_cur, st));
-
   // ---- R-Net on the measurement (KVNET.py:134) ----------------------------------------------------
-  const float* feat_ref = feat.p + (size_t)V * featS;
+  const float* feat_ref = feat.p ? feat.p + (size_t)V * featS : nullptr;
   const float* l1_ref = l1.p ? l1.p + (size_t)V * 4 * hw * l1.Cs : nullptr;
-  Act frame_ref = x0; frame_ref.N = 1; frame_ref.p = x0.p ? x0.p + (size_t)V * HW * x0.Cs : nullptr;
-  const bool steady = bv_predict != nullptr;
-  if (dmap_cur_refined || (!steady && dmap_refined)) {
-    Act r = r_net(e, e->bv_cur_hwd, feat_ref, feat.Cs, l1_ref, l1.Cs, frame_ref);
-    if (dmap_cur_refined) ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_cur_refined, st));
-    if (!steady && dmap_refined) ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_refined, st));
-    release(e, r);
-  }
+  Act frame_ref = x0; frame_ref.N = 1; frame_ref.p = x0.p + (size_t)V * HW * x0.Cs;
+  Act out_cur; out_cur.p = e->ref_cur_hwd; out_cur.N = 1; out_cur.D = 1; out_cur.H = H; out_cur.W = W; out_cur.C = D; out_cur.Cs = D;
+  Act out_kv = out_cur; out_kv.p = e->ref_kv_hwd;
+  if (need_cur_refined) r_net(e, e->bv_cur_hwd, feat_ref, feat.Cs, l1_ref, l1.Cs, frame_ref, out_cur);
   if (!steady) {
     // first window: DPV = BV_cur (KVNET.py:138-140)
     if (!e->rc) cudaMemcpyAsync(e->dpv_hwd, e->bv_cur_hwd, sizeof(float) * hw * D, cudaMemcpyDeviceToDevice, e->st);
-    if (dpv) ENG_CALL(e, nrgbd_transpose2d(e->bv_cur_hwd, (int)hw, D, dpv, st));
   } else {
     // ---- K-Net (KVNET.py:147-173) ------------------------------------------------------------------
     const Camera& c1 = e->cam[1];
     const int CK = 3 * V + 4;
-    ENG_CALL(e, nrgbd_transpose2d(bv_predict, D, (int)hw, e->prior_hwd, st));
     Act vol = acquire(e, 1, D, h, w, CK);
     ENG_CALL(e, nrgbd_knet_input_volume(rgbq.p, rgbq.p + (size_t)V * hw * 4, e->bv_cur_hwd, e->prior_hwd, V, D, h, w, vol.Cs,
                                         c1.K, Rs, ts, c1.rays, e->d_planes, c1.cx, c1.cy, e->ws_sweep, vol.p, st));
@@ -648,17 +759,9 @@ int nrgbd_kvnet_forward(nrgbd_kvnet* e, const float* frames, const float* poses,
     ENG_CALL(e, nrgbd_dpv_normalize(gain.p, hw, 1, e->prior_hwd, 1, D, 1.f, (int)hw, D, e->dpv_hwd, 1, D, e->d_planes, e->depth,
                                     e->conf, st));
     release(e, gain);
-    if (dpv) ENG_CALL(e, nrgbd_transpose2d(e->dpv_hwd, (int)hw, D, dpv, st));
-    if (dmap_refined) {
-      Act r = r_net(e, e->dpv_hwd, feat_ref, feat.Cs, l1_ref, l1.Cs, frame_ref);
-      ENG_CALL(e, nrgbd_transpose2d(r.p, (int)HW, D, dmap_refined, st));
-      release(e, r);
-    }
+    if (need_kv_refined) r_net(e, e->dpv_hwd, feat_ref, feat.Cs, l1_ref, l1.Cs, frame_ref, out_kv);
   }
-  if (depth_lowres && !e->rc) cudaMemcpyAsync(depth_lowres, e->depth, sizeof(float) * hw, cudaMemcpyDeviceToDevice, e->st);
-  if (conf_lowres && !e->rc) cudaMemcpyAsync(conf_lowres, e->conf, sizeof(float) * hw, cudaMemcpyDeviceToDevice, e->st);
-  release(e, x0); release(e, l1); release(e, feat); release(e, rgbq);
-  if (Rt) e->pool.release(Rt);
+  release(e, l1); release(e, feat); release(e, rgbq);
   if (e->rc == 0) { cudaError_t ce = cudaGetLastError(); if (ce != cudaSuccess) { nrgbd_set_error("nrgbd_kvnet_forward: %s", cudaGetErrorString(ce)); e->rc = NRGBD_ERR_CUDA; } }
   return e->rc;
 }

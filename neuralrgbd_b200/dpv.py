@@ -5,6 +5,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._devcache import planes_tensor
 from ._lib import ptr, check
 
 _F = ctypes.c_float
@@ -26,7 +27,7 @@ def log_softmax_planes(x, sign=1.0, add=None, d_candi=None):
         out = torch.empty_like(a)
         dpl = depth = conf = None
         if d_candi is not None:
-            dpl = torch.from_numpy(np.asarray(d_candi).astype(np.float32)).to(a.device)
+            dpl = planes_tensor(d_candi, a.device)
             depth = torch.empty((1, H, W), device=a.device, dtype=torch.float32)
             conf = torch.empty((1, H, W), device=a.device, dtype=torch.float32)
         check(L.nrgbd_dpv_normalize(ptr(a), H * W, 1, ptr(b), H * W, 1, _F(sign), H * W, D, ptr(out), H * W, 1, ptr(dpl),

@@ -107,6 +107,7 @@ class KVNET(nn.Module):
             m = self._modules.pop(k)
             self._modules[k] = m
         self._engines = {}
+        self.register_state_dict_pre_hook(KVNET._flush_batches_tracked)
         print('KV-Net initialization:')
         print('with R-net: %r' % (self.if_refined))
         print('\trefinement name: %s' % (self.refineNet_name))
@@ -127,20 +128,37 @@ class KVNET(nn.Module):
             self._engines[key] = ent
         return ent
 
+    def _param_list(self):
+        """(name, tensor) for every float parameter / buffer the engine needs, cached per module object
+        (a DataParallel replica is a new object each forward and rebuilds it)."""
+        cache = self.__dict__.get('_plist')
+        if cache is None or cache[0] != id(self):
+            sd = dict(self.named_parameters())
+            sd.update({k: v for k, v in self.named_buffers()})
+            cache = (id(self), [(name, sd[name]) for name, shape, kind in self._specs if kind != 'bn_nb'])
+            self.__dict__['_plist'] = cache
+        return cache[1]
+
     def _sync_params(self, ent, device):
         L = _lib.lib()
-        sd = dict(self.named_parameters())
-        sd.update({k: v for k, v in self.named_buffers()})
-        for name, shape, kind in self._specs:
-            if kind == 'bn_nb':
-                continue
-            t = sd[name]
-            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
-                raise _lib.NrgbdError('parameter %s must be a contiguous float32 tensor on %s (call .cuda())' % (name, device))
+        seen = ent['params']
+        for name, t in self._param_list():
             tag = (t.data_ptr(), t._version)
-            if ent['params'].get(name) != tag:
+            if seen.get(name) != tag:
+                if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.NrgbdError('parameter %s must be a contiguous float32 tensor on %s (call .cuda())' % (name, device))
                 check(L.nrgbd_kvnet_set_param(ent['h'], name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), 1))
-                ent['params'][name] = tag
+                seen[name] = tag
+
+    def _flush_batches_tracked(self, *args, **kwargs):
+        """BatchNorm's num_batches_tracked side effect (training mode) is applied lazily: one counter per
+        forward on the host, materialised into the 15 buffers when the state_dict is read."""
+        n = self.__dict__.get('_nb_pending', 0)
+        if n:
+            for name, _, kind in self._specs:
+                if kind == 'bn_nb':
+                    self.get_buffer(name).add_(n)
+            self.__dict__['_nb_pending'] = 0
 
     def _set_camera(self, ent, slot, cam=None, IntM=None, rays=None):
         L = _lib.lib()
@@ -225,9 +243,7 @@ class KVNET(nn.Module):
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             check(L.nrgbd_kvnet_forward(ent['h'], ptr(frames), ptr(poses), ptr(prior), ptr(dmap_cur), ptr(dmap_kv),
                                         ptr(bv_cur), ptr(dpv), ptr(depth), ptr(conf), st))
-            for name, _, kind in self._specs:          # BatchNorm side effect in training mode
-                if kind == 'bn_nb':
-                    self.get_buffer(name).add_(1)
+            self.__dict__['_nb_pending'] = self.__dict__.get('_nb_pending', 0) + 1   # BatchNorm side effect, applied lazily
         if prior is None:
             out = (dmap_cur, dmap_cur, bv_cur, bv_cur)     # KVNET.py:138-143
         else:

@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from .._devcache import planes_tensor
 from .._lib import ptr, check
 
 
@@ -40,7 +41,7 @@ def depth_val_regression(BV_measure, d_candi_cur, BV_log=True, return_conf=False
     with torch.cuda.device(BV_measure.device):
         bv = BV_measure[0].float().contiguous()
         D, H, W = bv.shape
-        dpl = torch.from_numpy(np.asarray(d_candi_cur).astype(np.float32)).to(bv.device)
+        dpl = planes_tensor(d_candi_cur, bv.device)
         depth = torch.empty((1, H, W), device=bv.device, dtype=torch.float32)
         conf = torch.empty((1, H, W), device=bv.device, dtype=torch.float32) if return_conf else None
         check(L.nrgbd_depth_regression(ptr(bv), H * W, D, H * W, 1, ptr(dpl), 1 if BV_log else 0, ptr(depth),

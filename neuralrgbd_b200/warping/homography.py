@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from .._devcache import planes_tensor
 from .._lib import ptr, check
 
 _F = ctypes.c_float
@@ -48,7 +49,7 @@ def _cam_tensors(cam_intrinsic, device):
 
 def _planes(d_candi, device):
     # homography.py:311: torch.from_numpy(d_candi.astype(np.float32)).cuda()
-    return torch.from_numpy(np.asarray(d_candi).astype(np.float32)).to(device)
+    return planes_tensor(d_candi, device)
 
 
 def _stack_Rt(R, t, device):
@@ -220,7 +221,7 @@ def resample_vol_cuda(src_vol, rel_extM, cam_intrinsic=None, d_candi=None, d_can
         N, D, H, W = src_vol.shape
         K, rays = _cam_tensors(cam_intrinsic, dev)
         d_pts, tan_hh, tan_hv, z_half, z_radius = resample_params(cam_intrinsic, d_candi, d_candi_new)
-        dp = torch.from_numpy(d_pts).to(dev)
+        dp = planes_tensor(d_pts, dev)
         E = rel_extM.to(device=dev, dtype=torch.float32).contiguous()
         vol = src_vol.float().contiguous()
         out = torch.empty((D, H, W), device=dev, dtype=torch.float32)
