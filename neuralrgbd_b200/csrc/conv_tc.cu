@@ -38,9 +38,9 @@ struct TcParams {
   int Cout, Cout_pad;
   int Dout, Hout, Wout, Cs_out, c_off, out_stride, out_off_y, out_off_x;
   int leaky, stages, tmem_cols, nacc, dev_flags;   // nacc: rotating main accumulators (nm)
-  int nl;                            // (unused)
+  int nl;                            // v2: number of TMEM operand buffers (2 or 4)
   int n_issue;                       // MMA issue streams (warps): 1 or 2
-  long long* dbg;                    // optional [grid][8] clock64 timestamps (development)
+  long long* dbg;                    // optional [grid][64] clock64 timestamps (development)
   signed char dz[MAX_TAPS_TC], dy[MAX_TAPS_TC], dx[MAX_TAPS_TC];
   unsigned char wsel[MAX_TAPS_TC];
 };
@@ -69,6 +69,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Bounded spin: a protocol bug becomes a trap (error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 28); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -177,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 8 + 0] = t_start; p.dbg[blockIdx.x * 8 + 1] = clock64(); }
+  if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 64 + 0] = t_start; p.dbg[blockIdx.x * 64 + 1] = clock64(); }
 
   const int nk = p.n_taps * p.cin_chunks;
 
@@ -219,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int s = ks % p.stages;
         const uint32_t ph = (uint32_t)(ks / p.stages) & 1u;
         mbar_wait(bar_full + 8 * s, ph);
-        if (p.dbg && ks == 0 && lane == 0 && w == 0) p.dbg[blockIdx.x * 8 + 2] = clock64();      // first operands landed
+        if (p.dbg && ks == 0 && lane == 0 && w == 0) p.dbg[blockIdx.x * 64 + 2] = clock64();      // first operands landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * stage_bytes;
         const uint32_t d_main = d_base + (uint32_t)((ks % p.nacc) * BN);        // rotates per K-step (RZ drift)
@@ -245,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         __syncwarp();
       }
       umma_commit(bar_tmem);                      // this stream's accumulators are complete
-      if (p.dbg && lane == 0 && w == 0) p.dbg[blockIdx.x * 8 + 3] = clock64();      // all MMAs issued
+      if (p.dbg && lane == 0 && w == 0) p.dbg[blockIdx.x * 64 + 3] = clock64();      // all MMAs issued
     }
   } else if (warp >= 2 && warp <= 5) {
     // ===== epilogue (warps 2..5): TMEM lanes [32*(warp%4), +32) =====
@@ -259,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     float* ep = reinterpret_cast<float*>(smem_gen);          // [128][BN+1] staging, reuses the pipeline stages
     const int EPS = BN + 1;
     mbar_wait(bar_tmem, 0);
-    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 8 + 4] = clock64();   // accumulator complete
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 4] = clock64();   // accumulator complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool vec_ok = ((p.Cs_out | p.c_off) & 3) == 0;
     for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -308,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (p.leaky) x = x >= 0.f ? x : x * 0.01f;
         f[j] = (valid && co < p.Cout) ? x : 0.f;
       }
-      if (valid) {
+      if (valid && !(p.dev_flags & 32)) {
         if (vec_ok && c0 + 16 <= p.Cout) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -317,13 +318,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           for (int j = 0; j < 16; ++j) if (c0 + j < p.Cout) dst[c0 + j] = f[j];
         }
       }
-      if (p.stats) {
+      if (p.stats && !(p.dev_flags & 16)) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) ep[r * EPS + c0 + j] = f[j];
       }
     }
-    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 8 + 5] = clock64();   // outputs stored
-    if (p.stats) {
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 5] = clock64();   // outputs stored
+    if (p.stats && !(p.dev_flags & 16)) {
       asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
       const int e = threadIdx.x - 64;                        // 0..127
       for (int co = e; co < p.Cout; co += 128) {
@@ -341,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
   if (p.dbg && threadIdx.x == 32) {
     unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.dbg[blockIdx.x * 8 + 6] = clock64(); p.dbg[blockIdx.x * 8 + 7] = smid;
+    p.dbg[blockIdx.x * 64 + 6] = clock64(); p.dbg[blockIdx.x * 64 + 7] = smid;
   }
 }
 
@@ -359,7 +360,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 //             aempty[b] tcgen05.commit -> converter                (MMAs reading buffer b retired)
 //             tmem_full tcgen05.commit -> epilogue
 // ---------------------------------------------------------------------------------------------
-constexpr int NUM_THREADS2 = 224;
+constexpr int NUM_THREADS2 = 224;       // one converter/epilogue group (two CTAs per SM)
+constexpr int NUM_THREADS2_G2 = 352;    // + warps 7-10: second converter/epilogue group (one CTA per SM)
 constexpr int A_BUF_COLS = 64;                 // 32 hi + 32 lo columns per TMEM operand buffer
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -382,7 +384,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[30]), "r"(v[31]) : "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS2, 2)
+// GROUPS = number of 4-warp converter/epilogue groups. One warp per SM sub-partition issues an
+// instruction every ~4.7 cycles (measured: 174 SASS instructions of epilogue arithmetic = 818 cycles), so
+// with a single group both the operand conversion (~1000 cycles per K-step against a 768-cycle tensor
+// floor at N = 128) and the epilogue (~2400 cycles per 16-column chunk) are bound by one warp's issue
+// rate. With one CTA per SM a second group (warps 7-10) takes the odd K-steps / odd column chunks.
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS == 2 ? NUM_THREADS2_G2 : NUM_THREADS2, GROUPS == 2 ? 1 : 2)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi,
                 const __grid_constant__ CUtensorMap tm_b_lo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -393,9 +401,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t stage_bytes = A_TILE_BYTES + 2 * b_tile_bytes;
   const uint32_t bars = smem_base + p.stages * stage_bytes;
   const uint32_t bar_full = bars, bar_empty = bars + 8 * p.stages, bar_afull = bars + 16 * p.stages,
-                 bar_aempty = bar_afull + 16, bar_tmem = bar_afull + 32;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + p.stages * stage_bytes + 16 * p.stages + 40);
+                 bar_aempty = bar_afull + 32, bar_tmem = bar_afull + 64;     // up to 4 operand buffers
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + p.stages * stage_bytes + 16 * p.stages + 72);
 
+  const long long t_start = clock64();
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
   int t = blockIdx.x;
   const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -406,7 +415,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4 + p.n_issue); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_afull + 8 * b, 4); mbar_init(bar_aempty + 8 * b, p.n_issue); }
+    for (int b = 0; b < p.nl; ++b) { mbar_init(bar_afull + 8 * b, 4); mbar_init(bar_aempty + 8 * b, p.n_issue); }
     mbar_init(bar_tmem, p.n_issue);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a) : "memory");
@@ -421,22 +430,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 64 + 0] = t_start; p.dbg[blockIdx.x * 64 + 1] = clock64(); }
   const uint32_t acc_cols = (uint32_t)(p.n_issue * (p.nacc + 1) * BN);   // operand buffers live after the accumulators
   const int nk = p.n_taps * p.cin_chunks;
 
   if (warp == 0) {
     {
+      // Running counters, no division: each role is a single warp, and a lone warp issues one dependent
+      // instruction every ~4-5 cycles - a runtime % or / costs ~150 cycles of its K-step budget.
+      int s = 0, tap = 0, cc = 0;
+      uint32_t ph = 0;
       for (int ks = 0; ks < nk; ++ks) {
-        const int s = ks % p.stages;
-        const uint32_t ph = (uint32_t)(ks / p.stages) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         mbar_expect_tx(bar_full + 8 * s, stage_bytes);
-        const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
         const uint32_t sa = smem_base + s * stage_bytes;
         const int cx = ox0 * p.in_stride + p.dx[tap], cy = oy0 * p.in_stride + p.dy[tap], cz = z0 + p.dz[tap];
         tma_load_5d(sa, &tm_a, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
         tma_load_3d(sa + A_TILE_BYTES, &tm_b_hi, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
         tma_load_3d(sa + A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+        if (++cc == p.cin_chunks) { cc = 0; ++tap; }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1 || warp == 6) {
@@ -447,11 +460,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       const int k_lo = w * (BK / 8) / p.n_issue, k_hi = (w + 1) * (BK / 8) / p.n_issue;
       const uint32_t d_base = tmem_base + (uint32_t)(w * (p.nacc + 1) * BN);
       const uint32_t d_lo = d_base + (uint32_t)(p.nacc * BN);
+      int s = 0, b = 0, m = 0;
+      uint32_t sph = 0, bph = 0;
       for (int ks = 0; ks < nk; ++ks) {
-        const int s = ks % p.stages, b = ks & 1;
-        const uint32_t d_main = d_base + (uint32_t)((ks % p.nacc) * BN);
-        mbar_wait(bar_full + 8 * s, (uint32_t)(ks / p.stages) & 1u);        // weights landed
-        mbar_wait(bar_afull + 8 * b, (uint32_t)(ks >> 1) & 1u);             // operand buffer b written
+        const uint32_t d_main = d_base + (uint32_t)(m * BN);
+        mbar_wait(bar_full + 8 * s, sph);             // weights landed
+        mbar_wait(bar_afull + 8 * b, bph);            // operand buffer b written
+        const bool tr = p.dbg && lane == 0 && w == 0 && ks >= 8 && ks < 14;
+        if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 4] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * stage_bytes;
         const uint32_t a_hi0 = tmem_base + acc_cols + (uint32_t)(b * A_BUF_COLS);
@@ -471,17 +487,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           umma_commit_raw(bar_empty + 8 * s);      // weights of stage s consumed by this stream
           umma_commit_raw(bar_aempty + 8 * b);     // operand buffer b consumed by this stream
         }
+        if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 5] = clock64();
         __syncwarp();
+        if (++s == p.stages) { s = 0; sph ^= 1u; }
+        if (++b == p.nl) { b = 0; bph ^= 1u; }
+        if (++m == p.nacc) m = 0;
       }
       umma_commit(bar_tmem);
     }
-  } else if (warp >= 2 && warp <= 5) {
-    const int q = warp & 3;
+  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+    const int cg = warp >= 7 ? 1 : 0;             // converter / epilogue group
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                  // GEMM row = TMEM lane = pixel within the tile
-    // ===== operand converter =====
-    for (int ks = 0; ks < nk; ++ks) {
-      const int s = ks % p.stages, b = ks & 1;
-      mbar_wait(bar_full + 8 * s, (uint32_t)(ks / p.stages) & 1u);
+    // ===== operand converter: group cg owns K-steps cg, cg + GROUPS, ... (= operand buffer cg when GROUPS == 2) =====
+    int s = cg, b = cg;                           // stages >= 2 and nl >= 2 >= GROUPS
+    uint32_t sph = 0, bph = 0;
+    for (int ks = cg; ks < nk; ks += GROUPS) {
+      mbar_wait(bar_full + 8 * s, sph);
+      const bool tr = p.dbg && threadIdx.x == 64 && ks >= 8 && ks < 14;
+      if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 0] = clock64();
       const uint8_t* row = smem_gen + (size_t)s * stage_bytes + (size_t)r * 128;
       uint32_t hi[32], lo[32];
 #pragma unroll
@@ -499,7 +523,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);                        // this warp is done with the raw tile
-      mbar_wait(bar_aempty + 8 * b, ((uint32_t)(ks >> 1) & 1u) ^ 1u);        // MMAs that read buffer b have retired
+      if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 1] = clock64();
+      mbar_wait(bar_aempty + 8 * b, bph ^ 1u);      // MMAs that read buffer b have retired
+      if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 2] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)(b * A_BUF_COLS);
       tmem_st32(ta, hi);
@@ -508,6 +534,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_afull + 8 * b);
+      if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 3] = clock64();
+      s += GROUPS; if (s >= p.stages) { s -= p.stages; sph ^= 1u; }
+      b += GROUPS; if (b >= p.nl) { b -= p.nl; bph ^= 1u; }
     }
     // ===== epilogue =====
     const int py = r / TW, px = r % TW;
@@ -517,29 +546,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     float* dst = p.y + ((((long long)n0 * p.Dout + z0) * p.Hout + oy) * p.Wout + ox) * (long long)p.Cs_out + p.c_off;
     float* ep = reinterpret_cast<float*>(smem_gen);
     const int EPS = BN + 1;
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 3] = clock64();   // converter done
     mbar_wait(bar_tmem, 0);
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 4] = clock64();   // accumulators complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool vec_ok = ((p.Cs_out | p.c_off) & 3) == 0;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    // accumulator slots that were written: per issue stream nacc rotating mains (only min(nk, nacc) of them
+    // used) + one cross-term accumulator
+    const int per = p.nacc + 1;
+    const int n_slots = p.n_issue * per;
+    uint32_t slot_mask = 0;
+    {
+      const int used_m = nk < p.nacc ? nk : p.nacc;
+      for (int a = 0; a < n_slots; ++a) if (a % per < used_m || a % per == p.nacc) slot_mask |= 1u << a;
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = cg * 16; c0 < BN; c0 += 16 * GROUPS) {
       float accv[16];
+      const bool stamp = p.dbg && threadIdx.x == 64 && c0 == 16 * GROUPS;
+      if (stamp) p.dbg[blockIdx.x * 64 + 8] = clock64();
       {
-        // accumulator order: cross-term accumulators first (small), then the main chains; fetched
-        // four at a time back to back with one wait
-        const int per = p.nacc + 1;                         // accumulators per issue stream: nacc mains + cross terms
-        const int used_m = nk < p.nacc ? nk : p.nacc;       // mains actually written (rotation per K-step)
-        const int n_acc = p.n_issue * (used_m + 1);
 #pragma unroll
         for (int j = 0; j < 16; ++j) accv[j] = 0.f;
 #pragma unroll 1
-        for (int a0 = 0; a0 < n_acc; a0 += 4) {
+        for (int a0 = 0; a0 < n_slots; a0 += 4) {
           uint32_t v[4][16];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (a0 + u < n_acc) {
-              const int idx = a0 + u;
-              // cross-term accumulators first (small), then the mains of every stream
-              const int slot = (idx < p.n_issue) ? idx * per + p.nacc : ((idx - p.n_issue) / used_m) * per + (idx - p.n_issue) % used_m;
-              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0);
+            if ((slot_mask >> (a0 + u)) & 1u) {
+              const uint32_t taddr = lane_base + (uint32_t)((a0 + u) * BN + c0);
               asm volatile(
                   "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                   : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]), "=r"(v[u][4]), "=r"(v[u][5]), "=r"(v[u][6]),
@@ -551,22 +586,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (a0 + u < n_acc) {
+            if ((slot_mask >> (a0 + u)) & 1u) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(v[u][j]);
             }
         }
       }
-      float f[16];
+      if (stamp) p.dbg[blockIdx.x * 64 + 9] = clock64();
+      // branches, not selects: the common case (no bias, full chunk, pixel inside the image) executes nothing
+      float* f = accv;
+      if (p.bias) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = accv[j];
-        const int co = c0 + j;
-        if (p.bias && co < p.Cout) x += __ldg(p.bias + co);
-        if (p.leaky) x = x >= 0.f ? x : x * 0.01f;
-        f[j] = (valid && co < p.Cout) ? x : 0.f;
+        for (int j = 0; j < 16; ++j) if (c0 + j < p.Cout) f[j] += __ldg(p.bias + c0 + j);
       }
-      if (valid) {
+      if (p.leaky) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * 0.01f;
+      }
+      if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+      } else if (c0 + 16 > p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (c0 + j >= p.Cout) f[j] = 0.f;
+      }
+      if (stamp) p.dbg[blockIdx.x * 64 + 10] = clock64();
+      if (valid && !(p.dev_flags & 32)) {
         if (vec_ok && c0 + 16 <= p.Cout) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -575,17 +620,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           for (int j = 0; j < 16; ++j) if (c0 + j < p.Cout) dst[c0 + j] = f[j];
         }
       }
-      if (p.stats) {
+      if (stamp) p.dbg[blockIdx.x * 64 + 11] = clock64();
+      if (p.stats && !(p.dev_flags & 16)) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) ep[r * EPS + c0 + j] = f[j];
       }
+      if (stamp) p.dbg[blockIdx.x * 64 + 12] = clock64();
     }
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 64;
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 5] = clock64();   // outputs stored
+    if (p.stats && !(p.dev_flags & 16)) {
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * GROUPS) : "memory");     // the epilogue warps only
+      // group cg sums rows [cg * 128 / GROUPS, (cg + 1) * 128 / GROUPS) of every column
+      const int e = q * 32 + lane;
+      const int r_lo = cg * (128 / GROUPS), r_hi = r_lo + 128 / GROUPS;
       for (int co = e; co < p.Cout; co += 128) {
         float s1 = 0.f, s2 = 0.f;
-        for (int rr = 0; rr < 128; ++rr) { float x = ep[rr * EPS + co]; s1 += x; s2 = fmaf(x, x, s2); }
+        for (int rr = r_lo; rr < r_hi; ++rr) { float x = ep[rr * EPS + co]; s1 += x; s2 = fmaf(x, x, s2); }
         atomicAdd(p.stats + co, (double)s1);
         atomicAdd(p.stats + p.Cout + co, (double)s2);
       }
@@ -595,6 +645,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+  if (p.dbg && threadIdx.x == 32) {
+    unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.dbg[blockIdx.x * 64 + 6] = clock64(); p.dbg[blockIdx.x * 64 + 7] = smid;
   }
 }
 
@@ -627,7 +681,7 @@ mma_probe_kernel(int BN, int n_mma, int pattern, int nd, int grp, int two_warps,
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
   long long t0 = 0;
-  if (warp == 1 || (two_warps && warp == 2)) {
+  if (pattern < 10 && (warp == 1 || (two_warps && warp == 2))) {
     const int w = warp == 1 ? 0 : 1;
     t0 = clock64();
     if (pattern == 3) {          // lean issue stream: one elect per 12 MMAs, immediate descriptor advance
@@ -655,6 +709,40 @@ mma_probe_kernel(int BN, int n_mma, int pattern, int nd, int grp, int two_warps,
     mbar_wait(bar, 0);
     const long long t2 = clock64();
     if (lane == 0 && w == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+  }
+  if (pattern >= 10) {
+    // TMEM read-back probe: every warp reads its 32 lanes, n_mma loads of 16 / 32 / 64 columns, one wait each
+    // (pattern 10/11/12) or one wait at the end (pattern 13: x16, 14: x32)
+    __syncthreads();
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    float acc = 0.f;
+    const long long a0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t col = (uint32_t)((i * 64) & 255);
+      if (pattern == 10 || pattern == 13) {
+        uint32_t v[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(lane_base + col) : "memory");
+        if (pattern == 10) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += __uint_as_float(v[j]);
+      } else {
+        uint32_t v[32];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                       "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                       "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(lane_base + col) : "memory");
+        if (pattern == 11) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += __uint_as_float(v[j]);
+      }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const long long a1 = clock64();
+    if (threadIdx.x == 0) { out[0] = a1 - a0; out[1] = (long long)acc; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -840,33 +928,41 @@ int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, in
   // Resource plan: Cout_pad <= 64 -> two CTAs per SM (one issue stream, 2 accumulators + 2 operand
   // buffers = 256 TMEM columns, 3 x 32 KB stages); otherwise one CTA per SM.
   const bool two_per_sm = p.Cout_pad <= 64 && !(g_dev_flags & 2);
-  const int tmem_budget = (two_per_sm ? 256 : 512) - 2 * A_BUF_COLS;
+  // Operand buffers: the chain "buffer freed -> tcgen05.st of the next operands -> MMAs issued -> MMAs retired"
+  // is ~1100 cycles per K-step, longer than the 768-cycle tensor time of a K-step at N = 128, so with two
+  // buffers the tensor pipe idles a third of the time. One CTA per SM: four buffers when two accumulators
+  // (one main + the cross terms) still fit beside them.
+  int nbuf = (!two_per_sm && !(g_dev_flags & 128) && 2 * p.Cout_pad + 4 * A_BUF_COLS <= 512) ? 4 : 2;
+  const int tmem_budget = (two_per_sm ? 256 : 512) - nbuf * A_BUF_COLS;
   int n_issue = ((g_dev_flags & 8) && 4 * p.Cout_pad <= tmem_budget) ? 2 : 1;
   int nm = tmem_budget / (n_issue * p.Cout_pad) - 1;
   if (nm > 4) nm = 4;
   if (nm < 1) { nrgbd_set_error("conv_tc2: Cout too large for the TMEM operand buffers"); return NRGBD_ERR_UNSUPPORTED; }
   if (g_force_nacc > 0 && g_force_nacc < nm) nm = g_force_nacc;
-  p.n_issue = n_issue; p.nacc = nm; p.nl = 1;
-  int cols = 32; while (cols < n_issue * (nm + 1) * p.Cout_pad + 2 * A_BUF_COLS) cols <<= 1;
+  p.n_issue = n_issue; p.nacc = nm; p.nl = nbuf;
+  int cols = 32; while (cols < n_issue * (nm + 1) * p.Cout_pad + nbuf * A_BUF_COLS) cols <<= 1;
   p.tmem_cols = cols;
   const size_t stage = (size_t)A_TILE_BYTES + 2 * (size_t)p.Cout_pad * BK * 4;
   int stages = two_per_sm ? 3 : (int)((220 * 1024 - 2048) / stage);
   if (stages > 4) stages = 4;
   if (g_force_stages > 0 && g_force_stages < stages) stages = g_force_stages;
-  p.dev_flags = g_dev_flags; p.dbg = nullptr;
+  p.dev_flags = g_dev_flags; p.dbg = g_dbg;
   if (stages < 2) { nrgbd_set_error("conv_tc2: Cout too large for the shared-memory pipeline"); return NRGBD_ERR_UNSUPPORTED; }
   p.stages = stages;
   size_t ep_bytes = (size_t)128 * (p.Cout_pad + 1) * 4;
   size_t smem = (size_t)stages * stage + 1024 + 256;
   if (stages * stage < ep_bytes) smem = ep_bytes + 1024 + 256;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool two_groups = !two_per_sm && !(g_dev_flags & 64);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[two_groups]) {
+    cudaError_t e = two_groups ? cudaFuncSetAttribute(conv_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { nrgbd_set_error("conv_tc2: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return NRGBD_ERR_CUDA; }
-    configured = smem;
+    configured[two_groups] = smem;
   }
   const long long tiles = (long long)N * p.Dz * p.tiles_x * p.tiles_y;
-  conv_tc2_kernel<<<(unsigned)tiles, NUM_THREADS2, smem, st>>>(ta, tb_hi, tb_lo, p);
+  if (two_groups) conv_tc2_kernel<2><<<(unsigned)tiles, NUM_THREADS2_G2, smem, st>>>(ta, tb_hi, tb_lo, p);
+  else conv_tc2_kernel<1><<<(unsigned)tiles, NUM_THREADS2, smem, st>>>(ta, tb_hi, tb_lo, p);
   return NRGBD_OK;
 }
 

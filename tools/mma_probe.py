@@ -21,3 +21,10 @@ for BN in (32, 64, 128, 256):
             torch.cuda.synchronize()
             t = out.cpu().numpy()
             print('%-3d %-22s %4d  %8.1f %17.1f %12.1f' % (BN, name, ctas, t[0] / n, t[1] / n, 128 * BN * 8 / 2048.0))
+
+print('TMEM read-back: cycles per load (4 warps, 128 lanes)')
+for pat, name in ((10, 'x16, wait each'), (13, 'x16, one wait'), (11, 'x32, wait each'), (14, 'x32, one wait')):
+    for _ in range(2):
+        check(L.nrgbd_mma_probe(64, 256, pat, 1, 1, 0, 1, ctypes.c_void_p(out.data_ptr()), st))
+    torch.cuda.synchronize()
+    print('  %-16s %8.1f' % (name, out.cpu().numpy()[0] / 256.0))
