@@ -300,6 +300,19 @@ def run_engine(args):
     p1.record(stream)
     torch.cuda.synchronize()
     prof_ms_total = p0.elapsed_time(p1)
+    if args.layer_table and rank == 0:
+        # per-shape conv table of the profiling pass (ms per frame, TFLOP/s algorithmic) for DESIGN.md / profiles/
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(L.nrgbd_kvnet_profile_table(hnd, 0, buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            tag, n, ms, work = line.split(';')
+            rows.append({'layer': tag, 'launches_per_frame': int(n) // P_PROF, 'ms_per_frame': float(ms) / P_PROF,
+                         'algorithmic_tflops': float(work) / (float(ms) * 1e-3) / 1e12})
+        rows.sort(key=lambda r: -r['ms_per_frame'])
+        with open(args.layer_table, 'w') as f:
+            json.dump({'note': 'conv launches of one 640x480 D=64 V=4 frame, CUDA events around each launch in %d eager frames' % P_PROF,
+                       'frame_ms_eager': prof_ms_total / P_PROF, 'layers': rows}, f, indent=1)
     check(L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
     conv_ms, conv_flops, conv_n = ms_c.value, wk_c.value, n_c.value
     check(L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
@@ -407,6 +420,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layer-table', default=None, help='write the per-shape conv table of the profiling pass to this JSON file')
     ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight on separate streams (resident-value loop)')
     ap.add_argument('--conv-math', default='tf32x3', choices=['fp32', 'tf32x3'],
                     help='fp32: exact CUDA-core FFMA implicit GEMM; tf32x3: tcgen05 error-compensated 3xTF32 (default)')

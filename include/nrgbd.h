@@ -207,6 +207,10 @@ int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value);   /* "bn
 /* with option "profile"=1 the engine brackets its conv (category 0, work = flops) and plane-sweep
  * (category 1, work = algorithmic bytes) launches with CUDA events; this returns and clears the sums. */
 int nrgbd_kvnet_profile_read(nrgbd_kvnet* e, int category, double* ms, double* work, long long* launches);
+
+/* Development aid: per-shape table of the profiled launches of one category, text lines
+ * "tag;launches;total_ms;work" written NUL-terminated into buf (truncated to cap). Records are kept. */
+int nrgbd_kvnet_profile_table(nrgbd_kvnet* e, int category, char* buf, long long cap);
 long long nrgbd_kvnet_workspace_bytes(nrgbd_kvnet* e);
 /* frames [V+1][3][H][W] (sources then reference), poses [V][4][4], bv_predict [D][h][w] or NULL
  * (first window). Outputs (any may be NULL): dmap_cur_refined, dmap_refined [D][H][W] log-DPV;

@@ -75,6 +75,7 @@ SIGNATURES = {
     'nrgbd_kvnet_workspace_bytes': (c_ll, [c_vp]),
     'nrgbd_kvnet_profile_read': (c_int, [c_vp, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(c_ll)]),
+    'nrgbd_kvnet_profile_table': (c_int, [c_vp, c_int, ctypes.c_char_p, c_ll]),
     'nrgbd_kvnet_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'nrgbd_kvnet_propagate': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }

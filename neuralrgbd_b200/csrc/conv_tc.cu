@@ -18,6 +18,7 @@
 //   warps 2-5 epilogue: tcgen05.ld 32x32b (one output pixel per thread), bias / LeakyReLU, vector
 //             stores to the channels-last output, BatchNorm sum / sum-of-squares via a smem
 //             transpose and one double atomicAdd per channel per CTA.
+#include <cstdlib>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -40,6 +41,7 @@ struct TcParams {
   int leaky, stages, tmem_cols, nacc, dev_flags;   // nacc: rotating main accumulators (nm)
   int nl;                            // v2: number of TMEM operand buffers (2 or 4)
   int n_issue;                       // MMA issue streams (warps): 1 or 2
+  int tma_store;                     // v2: output tile leaves through a TMA tensor store (stride-1 outputs)
   long long* dbg;                    // optional [grid][64] clock64 timestamps (development)
   signed char dz[MAX_TAPS_TC], dy[MAX_TAPS_TC], dx[MAX_TAPS_TC];
   unsigned char wsel[MAX_TAPS_TC];
@@ -392,7 +394,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
 template <int GROUPS>
 __global__ void __launch_bounds__(GROUPS == 2 ? NUM_THREADS2_G2 : NUM_THREADS2, GROUPS == 2 ? 1 : 2)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi,
-                const __grid_constant__ CUtensorMap tm_b_lo, const TcParams p) {
+                const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ CUtensorMap tm_y, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -421,6 +423,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_lo) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_y) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -442,12 +445,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       uint32_t ph = 0;
       for (int ks = 0; ks < nk; ++ks) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+        const bool skip_b = (p.dev_flags & 512) != 0;      // timing experiments only (results are garbage)
+        mbar_expect_tx(bar_full + 8 * s, skip_b ? A_TILE_BYTES : stage_bytes);
         const uint32_t sa = smem_base + s * stage_bytes;
         const int cx = ox0 * p.in_stride + p.dx[tap], cy = oy0 * p.in_stride + p.dy[tap], cz = z0 + p.dz[tap];
         tma_load_5d(sa, &tm_a, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
-        tma_load_3d(sa + A_TILE_BYTES, &tm_b_hi, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
-        tma_load_3d(sa + A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+        if (!skip_b) {
+          tma_load_3d(sa + A_TILE_BYTES, &tm_b_hi, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+          tma_load_3d(sa + A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
+        }
         if (++cc == p.cin_chunks) { cc = 0; ++tap; }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -462,12 +468,61 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       const uint32_t d_lo = d_base + (uint32_t)(p.nacc * BN);
       int s = 0, b = 0, m = 0;
       uint32_t sph = 0, bph = 0;
+      if (p.n_issue == 1) {
+        // Single stream, software-pipelined: tcgen05.mma issue blocks at the tensor rate (the queue is short:
+        // 12 N=128 MMAs take ~770 cycles to issue), so anything this thread does between the last MMA of a
+        // K-step and the first of the next is tensor idle time (measured ~390 cycles per K-step). The waits
+        // and address arithmetic for K-step ks+1 therefore run before the last k-slice of K-step ks is issued,
+        // while the queue still holds work.
+        mbar_wait(bar_full, 0);
+        mbar_wait(bar_afull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ks = 0; ks < nk; ++ks) {
+          const uint32_t d_main = d_base + (uint32_t)(m * BN);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint32_t a_hi0 = tmem_base + acc_cols + (uint32_t)(b * A_BUF_COLS);
+          const uint32_t lb_hi = desc_lo(sa + A_TILE_BYTES), lb_lo = desc_lo(sa + A_TILE_BYTES + b_tile_bytes);
+          const uint32_t acc0 = ks > 0 ? 1u : 0u, accm0 = ks >= p.nacc ? 1u : 0u;
+          const uint32_t bar_e = bar_empty + 8 * s, bar_ae = bar_aempty + 8 * b;
+          const bool tr = p.dbg && lane == 0 && ks >= 8 && ks < 14;
+          if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 4] = clock64();
+          if (elect_one()) {
+            umma_tf32_ts_raw(d_lo, a_hi0 + 32, desc_of(lb_hi), idesc, acc0);
+            umma_tf32_ts_raw(d_lo, a_hi0, desc_of(lb_lo), idesc, 1u);
+            umma_tf32_ts_raw(d_main, a_hi0, desc_of(lb_hi), idesc, accm0);
+#pragma unroll
+            for (int k4 = 1; k4 < BK / 8 - 1; ++k4) {
+              umma_tf32_ts_raw(d_lo, a_hi0 + 32 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+              umma_tf32_ts_raw(d_lo, a_hi0 + k4 * 8, desc_of(lb_lo + 2 * k4), idesc, 1u);
+              umma_tf32_ts_raw(d_main, a_hi0 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+            }
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; sph ^= 1u; }
+          if (++b == p.nl) { b = 0; bph ^= 1u; }
+          if (++m == p.nacc) m = 0;
+          if (ks + 1 < nk) {
+            mbar_wait(bar_full + 8 * s, sph);           // weights of the next K-step landed
+            mbar_wait(bar_afull + 8 * b, bph);          // its operand buffer is written
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          if (elect_one()) {
+            constexpr int k4 = BK / 8 - 1;
+            umma_tf32_ts_raw(d_lo, a_hi0 + 32 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+            umma_tf32_ts_raw(d_lo, a_hi0 + k4 * 8, desc_of(lb_lo + 2 * k4), idesc, 1u);
+            umma_tf32_ts_raw(d_main, a_hi0 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+            umma_commit_raw(bar_e);        // weights of this stage consumed
+            umma_commit_raw(bar_ae);       // operand buffer consumed
+          }
+          if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 5] = clock64();
+          __syncwarp();
+        }
+      } else
       for (int ks = 0; ks < nk; ++ks) {
         const uint32_t d_main = d_base + (uint32_t)(m * BN);
+        const bool fresh_main = ks < p.nacc;           // first use of this main accumulator: overwrite
         mbar_wait(bar_full + 8 * s, sph);             // weights landed
         mbar_wait(bar_afull + 8 * b, bph);            // operand buffer b written
-        const bool tr = p.dbg && lane == 0 && w == 0 && ks >= 8 && ks < 14;
-        if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 4] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * stage_bytes;
         const uint32_t a_hi0 = tmem_base + acc_cols + (uint32_t)(b * A_BUF_COLS);
@@ -478,7 +533,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (k4 >= k_lo && k4 < k_hi) {
               const uint32_t a_hi = a_hi0 + k4 * 8, a_lo = a_hi0 + 32 + k4 * 8;
               const uint32_t acc = (ks > 0 || k4 > k_lo) ? 1u : 0u;
-              const uint32_t acc_m = (ks >= p.nacc || k4 > k_lo) ? 1u : 0u;
+              const uint32_t acc_m = (!fresh_main || k4 > k_lo) ? 1u : 0u;
               umma_tf32_ts_raw(d_lo, a_lo, desc_of(lb_hi + 2 * k4), idesc, acc);
               umma_tf32_ts_raw(d_lo, a_hi, desc_of(lb_lo + 2 * k4), idesc, 1u);
               umma_tf32_ts_raw(d_main, a_hi, desc_of(lb_hi + 2 * k4), idesc, acc_m);
@@ -487,7 +542,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           umma_commit_raw(bar_empty + 8 * s);      // weights of stage s consumed by this stream
           umma_commit_raw(bar_aempty + 8 * b);     // operand buffer b consumed by this stream
         }
-        if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 5] = clock64();
         __syncwarp();
         if (++s == p.stages) { s = 0; sph ^= 1u; }
         if (++b == p.nl) { b = 0; bph ^= 1u; }
@@ -508,9 +562,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 0] = clock64();
       const uint8_t* row = smem_gen + (size_t)s * stage_bytes + (size_t)r * 128;
       uint32_t hi[32], lo[32];
+      const bool skip_lds = (p.dev_flags & 1024) != 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {               // 16-byte chunk j of this row sits at chunk (j ^ (r & 7))
-        const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+        const float4 v = skip_lds ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
         const float a[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -528,8 +583,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 2] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)(b * A_BUF_COLS);
-      tmem_st32(ta, hi);
-      tmem_st32(ta + 32, lo);
+      if (!(p.dev_flags & 256)) {
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -544,8 +601,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const bool valid = iy < p.Hy && ix < p.Wx;
     const int oy = iy * p.out_stride + p.out_off_y, ox = ix * p.out_stride + p.out_off_x;
     float* dst = p.y + ((((long long)n0 * p.Dout + z0) * p.Hout + oy) * p.Wout + ox) * (long long)p.Cs_out + p.c_off;
-    float* ep = reinterpret_cast<float*>(smem_gen);
-    const int EPS = BN + 1;
+    // Output staging: the finished tile is written to shared memory as BN/32 slabs of [128 pixels][32 channels]
+    // in the 128-byte-swizzled layout of a TMA box (the mirror image of the operand tile), from where (a) one
+    // thread sends it to global memory with cp.async.bulk.tensor stores - coalesced, clipped at the image and
+    // channel bounds by the tensor map, instead of 16-byte stores scattered over 32 lines per instruction
+    // (measured ~1000 cycles per 16-column chunk with eight warps storing) - and (b) the BatchNorm column
+    // sums are read conflict-free.
+    uint8_t* ep = smem_gen;
+    const bool tma_out = p.tma_store != 0 && !(p.dev_flags & 32);
+    const bool want_stats = p.stats && !(p.dev_flags & 16);
     if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 3] = clock64();   // converter done
     mbar_wait(bar_tmem, 0);
     if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 4] = clock64();   // accumulators complete
@@ -561,9 +625,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       for (int a = 0; a < n_slots; ++a) if (a % per < used_m || a % per == p.nacc) slot_mask |= 1u << a;
     }
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = cg * 16; c0 < BN; c0 += 16 * GROUPS) {
+    // group cg owns the 32-channel slabs cg, cg + GROUPS, ...: as soon as a slab is staged its TMA store is issued,
+    // so the stores overlap the TMEM read-back of the following slabs
+    const bool storer = tma_out && q == 0 && lane == 0;            // one thread per group
+    for (int c0 = cg * 32; c0 < BN; c0 += ((c0 & 16) ? 32 * GROUPS - 16 : 16)) {
       float accv[16];
-      const bool stamp = p.dbg && threadIdx.x == 64 && c0 == 16 * GROUPS;
+      const bool stamp = p.dbg && threadIdx.x == 64 && c0 == 16;
       if (stamp) p.dbg[blockIdx.x * 64 + 8] = clock64();
       {
 #pragma unroll
@@ -611,7 +678,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int j = 0; j < 16; ++j) if (c0 + j >= p.Cout) f[j] = 0.f;
       }
       if (stamp) p.dbg[blockIdx.x * 64 + 10] = clock64();
-      if (valid && !(p.dev_flags & 32)) {
+      if (tma_out || want_stats) {
+        uint8_t* rowp = ep + (c0 >> 5) * 16384 + r * 128;
+        const int j0 = (c0 & 31) >> 2;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<float4*>(rowp + (((j0 + jj) ^ (r & 7)) << 4)) = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
+      }
+      if (stamp) p.dbg[blockIdx.x * 64 + 11] = clock64();
+      if (valid && !tma_out && !(p.dev_flags & 32)) {
         if (vec_ok && c0 + 16 <= p.Cout) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -620,25 +695,46 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           for (int j = 0; j < 16; ++j) if (c0 + j < p.Cout) dst[c0 + j] = f[j];
         }
       }
-      if (stamp) p.dbg[blockIdx.x * 64 + 11] = clock64();
-      if (p.stats && !(p.dev_flags & 16)) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ep[r * EPS + c0 + j] = f[j];
-      }
       if (stamp) p.dbg[blockIdx.x * 64 + 12] = clock64();
-    }
-    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 5] = clock64();   // outputs stored
-    if (p.stats && !(p.dev_flags & 16)) {
-      asm volatile("bar.sync 1, %0;" ::"n"(128 * GROUPS) : "memory");     // the epilogue warps only
-      // group cg sums rows [cg * 128 / GROUPS, (cg + 1) * 128 / GROUPS) of every column
-      const int e = q * 32 + lane;
-      const int r_lo = cg * (128 / GROUPS), r_hi = r_lo + 128 / GROUPS;
-      for (int co = e; co < p.Cout; co += 128) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int rr = r_lo; rr < r_hi; ++rr) { float x = ep[rr * EPS + co]; s1 += x; s2 = fmaf(x, x, s2); }
-        atomicAdd(p.stats + co, (double)s1);
-        atomicAdd(p.stats + p.Cout + co, (double)s2);
+      if (tma_out && ((c0 & 16) || c0 + 16 >= BN)) {       // last chunk of this slab
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged slab -> visible to the TMA engine
+        if (cg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int sl = c0 >> 5;
+        if (storer && sl * 32 < p.Cout) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"((uint64_t)&tm_y), "r"(smem_base + (uint32_t)(sl * 16384)), "r"(p.c_off + sl * 32), "r"(ox0), "r"(oy0), "r"(z0), "r"(n0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
+    }
+    if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 64 + 5] = clock64();   // outputs staged / stored
+    if (tma_out || want_stats) {
+      if (want_stats) {
+        asm volatile("bar.sync 3, %0;" ::"n"(128 * GROUPS) : "memory");            // every slab staged (epilogue warps only)
+        // column sums: the 128 * GROUPS epilogue threads split every column into row segments so that all of
+        // them work whatever Cout is (e.g. 64 channels, 128 threads: two 64-row segments per column)
+        const int e = cg * 128 + q * 32 + lane;
+        const int cw = (p.Cout + 31) & ~31;                       // columns rounded up to whole warps
+        const int nseg = cw <= 32 ? (128 * GROUPS) / 32 : cw <= 64 ? (128 * GROUPS) / 64 : cw <= 128 ? GROUPS : 1;
+        const int seg_rows = 128 / nseg;
+        const int co = e % cw, seg = e / cw;
+        if (cw <= 128 ? (seg < nseg && co < p.Cout) : false) {
+          const uint8_t* colp = ep + (co >> 5) * 16384 + (co & 3) * 4;
+          const int jc = (co & 31) >> 2;
+          float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll 4
+          for (int rr = seg * seg_rows; rr < (seg + 1) * seg_rows; rr += 2) {
+            const float x0 = *reinterpret_cast<const float*>(colp + rr * 128 + ((jc ^ (rr & 7)) << 4));
+            const float x1 = *reinterpret_cast<const float*>(colp + (rr + 1) * 128 + ((jc ^ ((rr + 1) & 7)) << 4));
+            s1 += x0; s2 = fmaf(x0, x0, s2);
+            t1 += x1; t2 = fmaf(x1, x1, t2);
+          }
+          atomicAdd(p.stats + co, (double)(s1 + t1));
+          atomicAdd(p.stats + p.Cout + co, (double)(s2 + t2));
+        }
+      }
+      if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the store's reads
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -692,6 +788,18 @@ mma_probe_kernel(int BN, int n_mma, int pattern, int nd, int grp, int two_warps,
 #pragma unroll
           for (int j = 0; j < 12; ++j)
             umma_tf32_raw(d0 + (uint32_t)((nd > 1 && (j % 3) != 2) ? BN : 0), desc_of(la + 2 * (j & 3)), desc_of(lb + 2 * (j & 3)), idesc, (i + j) >= 3 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+    } else if (pattern == 4) {   // lean TS stream: A operand from TMEM columns 384.. (contents irrelevant for timing)
+      const uint32_t lb = desc_lo(b_addr);
+      const uint32_t d0 = tmem_base + (uint32_t)(w * nd * BN), ta = tmem_base + 384u;
+      for (int i = 0; i < n_mma; i += 12) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j)
+            umma_tf32_ts_raw(d0 + (uint32_t)((nd > 1 && (j % 3) != 2) ? BN : 0), ta + 8 * (j & 3) + 32 * ((j % 3) == 0), desc_of(lb + 2 * (j & 3)), idesc,
+                             (i + j) >= 3 ? 1u : 0u);
         }
         __syncwarp();
       }
@@ -791,7 +899,9 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int kind, int
 int g_force_nacc = 0;
 int g_force_stages = 0;     // development knobs (nrgbd_conv_tc_set_dev)
 long long* g_dbg = nullptr;
-int g_dev_flags = 0;        // bit0: 1xTF32 (hi*hi only; v1: the lo tiles are not even loaded)      // development knob (nrgbd_conv_tc_set_nacc): cap on the main accumulators
+// development A/B switch without recompiling: NRGBD_TC_DEV=<flags> in the environment seeds g_dev_flags
+int env_dev_flags() { const char* v = getenv("NRGBD_TC_DEV"); return v ? atoi(v) : 0; }
+int g_dev_flags = env_dev_flags();        // bit0: 1xTF32 (hi*hi only; v1: the lo tiles are not even loaded)      // development knob (nrgbd_conv_tc_set_nacc): cap on the main accumulators
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -949,9 +1059,18 @@ int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, in
   p.dev_flags = g_dev_flags; p.dbg = g_dbg;
   if (stages < 2) { nrgbd_set_error("conv_tc2: Cout too large for the shared-memory pipeline"); return NRGBD_ERR_UNSUPPORTED; }
   p.stages = stages;
-  size_t ep_bytes = (size_t)128 * (p.Cout_pad + 1) * 4;
+  size_t ep_bytes = (size_t)((p.Cout_pad + 31) / 32) * 16384;     // output staging slabs alias the pipeline stages
   size_t smem = (size_t)stages * stage + 1024 + 256;
   if (stages * stage < ep_bytes) smem = ep_bytes + 1024 + 256;
+  // TMA tensor store of the output tile: stride-1 outputs whose channel window starts on a 16-byte boundary
+  CUtensorMap ty = ta;
+  p.tma_store = 0;
+  if (p.out_stride == 1 && p.out_off_y == 0 && p.out_off_x == 0 && p.Cs_out % 4 == 0 && p.c_off % 4 == 0 &&
+      ((uintptr_t)p.y & 15) == 0 && !(g_dev_flags & 2048)) {
+    rc = encode_act_map(&ty, p.y, N, p.Dout, p.Hout, p.Wout, p.c_off + p.Cout, p.Cs_out, 1);
+    if (rc != NRGBD_OK) return rc;
+    p.tma_store = 1;
+  }
   const bool two_groups = !two_per_sm && !(g_dev_flags & 64);
   static size_t configured[2] = {0, 0};
   if (smem > configured[two_groups]) {
@@ -961,8 +1080,8 @@ int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, in
     configured[two_groups] = smem;
   }
   const long long tiles = (long long)N * p.Dz * p.tiles_x * p.tiles_y;
-  if (two_groups) conv_tc2_kernel<2><<<(unsigned)tiles, NUM_THREADS2_G2, smem, st>>>(ta, tb_hi, tb_lo, p);
-  else conv_tc2_kernel<1><<<(unsigned)tiles, NUM_THREADS2, smem, st>>>(ta, tb_hi, tb_lo, p);
+  if (two_groups) conv_tc2_kernel<2><<<(unsigned)tiles, NUM_THREADS2_G2, smem, st>>>(ta, tb_hi, tb_lo, ty, p);
+  else conv_tc2_kernel<1><<<(unsigned)tiles, NUM_THREADS2, smem, st>>>(ta, tb_hi, tb_lo, ty, p);
   return NRGBD_OK;
 }
 

@@ -7,7 +7,10 @@
 // stream: no Python between layers, no allocation after warm-up, activations channels-last.
 // Parameters are registered by their reference state_dict names (borrowed device pointers or
 // engine-owned copies of host arrays), so kvnet_*.tar checkpoints map one to one.
+#include <array>
 #include <cmath>
+#include <cstdio>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -106,7 +109,7 @@ struct nrgbd_kvnet {
   std::vector<GraphEnt> graphs;
   unsigned long long graph_clock = 0;
   int profile = 0;
-  struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+  struct ProfRec { cudaEvent_t a, b; int cat; double work; char tag[56]; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_free;
 };
@@ -129,8 +132,12 @@ cudaEvent_t prof_event(Eng* e) {
 }
 struct ProfScope {
   Eng* e; bool on; nrgbd_kvnet::ProfRec r;
-  ProfScope(Eng* e_, int cat, double work) : e(e_), on(e_->profile && e_->rc == 0 && e_->prof.size() < 200000) {
-    if (on) { r.a = prof_event(e); r.b = prof_event(e); r.cat = cat; r.work = work; cudaEventRecord(r.a, e->st); }
+  ProfScope(Eng* e_, int cat, double work, const char* tag = "") : e(e_), on(e_->profile && e_->rc == 0 && e_->prof.size() < 200000) {
+    if (on) {
+      r.a = prof_event(e); r.b = prof_event(e); r.cat = cat; r.work = work;
+      snprintf(r.tag, sizeof(r.tag), "%s", tag);
+      cudaEventRecord(r.a, e->st);
+    }
   }
   ~ProfScope() { if (on) { cudaEventRecord(r.b, e->st); e->prof.push_back(r); } }
 };
@@ -224,10 +231,12 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   if (e->rc) return y;
   if (want_stats) cudaMemsetAsync(e->stats, 0, sizeof(double) * 2 * Cout, e->st);
   const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
+  char tag[56];
+  snprintf(tag, sizeof(tag), "conv%dd k%d s%d d%d %d->%d %dx%dx%dx%d", kd > 1 ? 3 : 2, k, stride, dil, x.C, Cout, x.N, x.D, Ho, Wo);
   if (use_tc(e, x, Cout)) {
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, kd * k * k, false);
     if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {       // in-kernel split, no extra pass
-      ProfScope ps(e, 0, flops);
+      ProfScope ps(e, 0, flops, tag);
       ENG_CALL(e, nrgbd_conv_nhwc_tc2(x.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
                                       stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
                                       (nrgbd_stream_t)e->st));
@@ -236,7 +245,7 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
     Act xh, xl;
     split_act(e, x, xh, xl);
     if (!e->rc) {
-      ProfScope ps(e, 0, flops);
+      ProfScope ps(e, 0, flops, tag);
       ENG_CALL(e, nrgbd_conv_nhwc_tc(xh.p, xl.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
                                      stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
                                      (nrgbd_stream_t)e->st));
@@ -246,7 +255,7 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   }
   const Packed* pk = packw(e, wname, Cout, x.C, kd * k * k, false);
   if (e->rc) return y;
-  ProfScope ps(e, 0, flops);
+  ProfScope ps(e, 0, flops, tag);
   ENG_CALL(e, nrgbd_conv_nhwc(x.p, x.N, x.D, x.H, x.W, pk->Cin_pad, x.Cs, pk->w, b, Cout, pk->Cout_pad, kd, k, k, stride,
                               pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
                               (nrgbd_stream_t)e->st));
@@ -360,10 +369,12 @@ void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* 
   if (e->rc) return;
   nrgbd_stream_t st = (nrgbd_stream_t)e->st;
   const double flops = 2.0 * 4.0 * (double)x.H * x.W * Cout * x.C * 4;
+  char tag[56];
+  snprintf(tag, sizeof(tag), "convT k4 s2 %d->%d %dx%dx%d", x.C, Cout, x.N, 2 * x.H, 2 * x.W);
   if (use_tc(e, x, Cout)) {
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, 16, true);
     if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {
-      ProfScope ps(e, 0, flops);
+      ProfScope ps(e, 0, flops, tag);
       ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc_tc2(x.p, x.N, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, tb, Cout, pt->Cout_pad,
                                                        dst.p, dst.Cs, 0, 1, st));
       return;
@@ -371,7 +382,7 @@ void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* 
     Act xh, xl;
     split_act(e, x, xh, xl);
     if (!e->rc) {
-      ProfScope ps(e, 0, flops);
+      ProfScope ps(e, 0, flops, tag);
       ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc_tc(xh.p, xl.p, x.N, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, tb, Cout, pt->Cout_pad,
                                                       dst.p, dst.Cs, 0, 1, st));
     }
@@ -380,7 +391,7 @@ void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* 
   }
   const Packed* pk = packw(e, wname, Cout, x.C, 16, true);
   if (e->rc) return;
-  ProfScope ps(e, 0, flops);
+  ProfScope ps(e, 0, flops, tag);
   ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc(x.p, x.N, x.H, x.W, pk->Cin_pad, x.Cs, pk->w, tb, Cout, pk->Cout_pad, dst.p, dst.Cs, 0, 1, st));
 }
 
@@ -594,6 +605,30 @@ int nrgbd_kvnet_profile_read(nrgbd_kvnet* e, int category, double* ms, double* w
     e->ev_free.push_back(r.a); e->ev_free.push_back(r.b);
   }
   e->prof.swap(keep);
+  return NRGBD_OK;
+}
+
+// Per-shape table of the profiled launches of one category (development / DESIGN.md tables): text lines
+// "tag;launches;total_ms;work" aggregated by tag, written to buf (NUL-terminated, truncated to cap).
+// Does not clear the records.
+int nrgbd_kvnet_profile_table(nrgbd_kvnet* e, int category, char* buf, long long cap) {
+  NRGBD_REQUIRE(e && buf && cap > 0, "bad arguments");
+  std::map<std::string, std::array<double, 3>> agg;
+  for (auto& r : e->prof) {
+    if (r.cat != category) continue;
+    float t = 0.f;
+    NRGBD_CUDA_CHECK(cudaEventSynchronize(r.b));
+    NRGBD_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    auto& a = agg[r.tag];
+    a[0] += 1; a[1] += t; a[2] += r.work;
+  }
+  std::string out;
+  char line[160];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s;%d;%.6f;%.6e\n", kv.first.c_str(), (int)kv.second[0], kv.second[1], kv.second[2]);
+    out += line;
+  }
+  snprintf(buf, (size_t)cap, "%s", out.c_str());
   return NRGBD_OK;
 }
 

@@ -28,3 +28,14 @@ for pat, name in ((10, 'x16, wait each'), (13, 'x16, one wait'), (11, 'x32, wait
         check(L.nrgbd_mma_probe(64, 256, pat, 1, 1, 0, 1, ctypes.c_void_p(out.data_ptr()), st))
     torch.cuda.synchronize()
     print('  %-16s %8.1f' % (name, out.cpu().numpy()[0] / 256.0))
+
+print('queue depth: issue vs completion cycles of n back-to-back MMAs, lean stream, 1 CTA')
+print('BN  form  n_mma   issue_cycles  total_cycles')
+for BN in (64, 128):
+    for pat, name in ((3, 'SS'), (4, 'TS')):
+        for n in (12, 24, 48, 96, 384):
+            for _ in range(2):
+                check(L.nrgbd_mma_probe(BN, n, pat, 2, 1, 0, 1, ctypes.c_void_p(out.data_ptr()), st))
+            torch.cuda.synchronize()
+            t = out.cpu().numpy()
+            print('%-3d %-4s %5d %12d %12d' % (BN, name, n, t[1], t[0]))
