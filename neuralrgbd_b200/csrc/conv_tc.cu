@@ -42,6 +42,7 @@ struct TcParams {
   int nl;                            // v2: number of TMEM operand buffers (2 or 4)
   int n_issue;                       // MMA issue streams (warps): 1 or 2
   int tma_store;                     // v2: output tile leaves through a TMA tensor store (stride-1 outputs)
+  int stages_a;                      // v2: activation-ring depth (stages = weight-ring depth)
   long long* dbg;                    // optional [grid][64] clock64 timestamps (development)
   signed char dz[MAX_TAPS_TC], dy[MAX_TAPS_TC], dx[MAX_TAPS_TC];
   unsigned char wsel[MAX_TAPS_TC];
@@ -395,16 +396,26 @@ template <int GROUPS>
 __global__ void __launch_bounds__(GROUPS == 2 ? NUM_THREADS2_G2 : NUM_THREADS2, GROUPS == 2 ? 1 : 2)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi,
                 const __grid_constant__ CUtensorMap tm_b_lo, const __grid_constant__ CUtensorMap tm_y, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // Shared memory: [activation ring: stages_a x 16 KB][weight ring: stages x (hi | lo) tile][barriers].
+  // Two rings because the two operands live very differently long: a raw activation tile is free as soon as
+  // the converter warps have read it (TMA latency + ~700 cycles), a weight tile only when the MMAs that read
+  // it have retired (another ~2000 cycles) - and the K-step rate is ring depth / slot lifetime (measured:
+  // 2 -> 3 -> 4 joint stages = 62K -> 36K -> 31K cycles for the 128-channel layer). The 1024-byte alignment
+  // the swizzled tiles need is requested from the compiler instead of padded for: two CTAs per SM use every byte.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  uint8_t* smem_gen = smem_raw;
   const int BN = p.Cout_pad;
   const uint32_t b_tile_bytes = (uint32_t)BN * BK * 4;
-  const uint32_t stage_bytes = A_TILE_BYTES + 2 * b_tile_bytes;
-  const uint32_t bars = smem_base + p.stages * stage_bytes;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * p.stages, bar_afull = bars + 16 * p.stages,
-                 bar_aempty = bar_afull + 32, bar_tmem = bar_afull + 64;     // up to 4 operand buffers
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + p.stages * stage_bytes + 16 * p.stages + 72);
+  const uint32_t b_slot_bytes = 2 * b_tile_bytes;
+  const uint32_t b_ring = smem_base + (uint32_t)p.stages_a * A_TILE_BYTES;
+  const uint32_t ring_bytes = (uint32_t)p.stages_a * A_TILE_BYTES + (uint32_t)p.stages * b_slot_bytes;
+  const uint32_t bars = smem_base + ring_bytes;
+  // barriers: a_full[8] a_empty[8] b_full[8] b_empty[8] afull[4] aempty[4] tmem
+  const uint32_t bar_full = bars, bar_empty = bars + 64, bar_bfull = bars + 128, bar_bempty = bars + 192,
+                 bar_afull = bars + 256, bar_aempty = bars + 288, bar_tmem = bars + 320;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + ring_bytes + 328);
 
   const long long t_start = clock64();
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
@@ -416,7 +427,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int ox0 = tx * TW, oy0 = ty * TH;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4 + p.n_issue); }
+    for (int s = 0; s < p.stages_a; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 4); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, p.n_issue); }
     for (int b = 0; b < p.nl; ++b) { mbar_init(bar_afull + 8 * b, 4); mbar_init(bar_aempty + 8 * b, p.n_issue); }
     mbar_init(bar_tmem, p.n_issue);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -441,21 +453,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     {
       // Running counters, no division: each role is a single warp, and a lone warp issues one dependent
       // instruction every ~4-5 cycles - a runtime % or / costs ~150 cycles of its K-step budget.
-      int s = 0, tap = 0, cc = 0;
-      uint32_t ph = 0;
+      int sa = 0, sb = 0, tap = 0, cc = 0;
+      uint32_t pha = 0, phb = 0;
       for (int ks = 0; ks < nk; ++ks) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        const bool skip_b = (p.dev_flags & 512) != 0;      // timing experiments only (results are garbage)
-        mbar_expect_tx(bar_full + 8 * s, skip_b ? A_TILE_BYTES : stage_bytes);
-        const uint32_t sa = smem_base + s * stage_bytes;
         const int cx = ox0 * p.in_stride + p.dx[tap], cy = oy0 * p.in_stride + p.dy[tap], cz = z0 + p.dz[tap];
-        tma_load_5d(sa, &tm_a, bar_full + 8 * s, cc * BK, cx, cy, cz, n0);
-        if (!skip_b) {
-          tma_load_3d(sa + A_TILE_BYTES, &tm_b_hi, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
-          tma_load_3d(sa + A_TILE_BYTES + b_tile_bytes, &tm_b_lo, bar_full + 8 * s, cc * BK, 0, p.wsel[tap]);
-        }
+        mbar_wait(bar_empty + 8 * sa, pha ^ 1u);
+        const bool tr = p.dbg && lane == 0 && ks >= 8 && ks < 14;
+        if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 6] = clock64();
+        mbar_expect_tx(bar_full + 8 * sa, A_TILE_BYTES);
+        tma_load_5d(smem_base + sa * A_TILE_BYTES, &tm_a, bar_full + 8 * sa, cc * BK, cx, cy, cz, n0);
+        mbar_wait(bar_bempty + 8 * sb, phb ^ 1u);
+        if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 7] = clock64();
+        mbar_expect_tx(bar_bfull + 8 * sb, b_slot_bytes);
+        const uint32_t sbm = b_ring + sb * b_slot_bytes;
+        tma_load_3d(sbm, &tm_b_hi, bar_bfull + 8 * sb, cc * BK, 0, p.wsel[tap]);
+        tma_load_3d(sbm + b_tile_bytes, &tm_b_lo, bar_bfull + 8 * sb, cc * BK, 0, p.wsel[tap]);
         if (++cc == p.cin_chunks) { cc = 0; ++tap; }
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++sa == p.stages_a) { sa = 0; pha ^= 1u; }
+        if (++sb == p.stages) { sb = 0; phb ^= 1u; }
       }
     }
   } else if (warp == 1 || warp == 6) {
@@ -474,18 +489,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // K-step and the first of the next is tensor idle time (measured ~390 cycles per K-step). The waits
         // and address arithmetic for K-step ks+1 therefore run before the last k-slice of K-step ks is issued,
         // while the queue still holds work.
-        mbar_wait(bar_full, 0);
+        const bool concat = p.nacc == 1 && 2 * BN <= 256 && !(p.dev_flags & 4096);
+        const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((128u >> 4) << 24);
+        mbar_wait(bar_bfull, 0);
         mbar_wait(bar_afull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int ks = 0; ks < nk; ++ks) {
           const uint32_t d_main = d_base + (uint32_t)(m * BN);
-          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint32_t sbm = b_ring + s * b_slot_bytes;
           const uint32_t a_hi0 = tmem_base + acc_cols + (uint32_t)(b * A_BUF_COLS);
-          const uint32_t lb_hi = desc_lo(sa + A_TILE_BYTES), lb_lo = desc_lo(sa + A_TILE_BYTES + b_tile_bytes);
+          const uint32_t lb_hi = desc_lo(sbm), lb_lo = desc_lo(sbm + b_tile_bytes);
           const uint32_t acc0 = ks > 0 ? 1u : 0u, accm0 = ks >= p.nacc ? 1u : 0u;
-          const uint32_t bar_e = bar_empty + 8 * s, bar_ae = bar_aempty + 8 * b;
+          const uint32_t bar_e = bar_bempty + 8 * s, bar_ae = bar_aempty + 8 * b;
           const bool tr = p.dbg && lane == 0 && ks >= 8 && ks < 14;
           if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 4] = clock64();
+          if (concat) {
+            // one main accumulator: main | cross columns are adjacent and so are the hi | lo weight tiles, so
+            // a_hi x [b_hi | b_lo] is ONE MMA of width 2 BN (main and the a_hi*b_lo cross term), a_lo x b_hi a
+            // second one: 8 issue slots per K-step instead of 12 (a lone issuing thread tops out at ~48 cycles
+            // per MMA, above the 32-cycle tensor time of an N = 64 MMA)
+            // (the four wide MMAs first, then the narrow ones: alternating instruction shapes issue slower)
+            if (elect_one()) {
+#pragma unroll
+              for (int k4 = 0; k4 < BK / 8; ++k4)
+                umma_tf32_ts_raw(d_base, a_hi0 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc2, k4 == 0 ? acc0 : 1u);
+#pragma unroll
+              for (int k4 = 0; k4 < BK / 16; ++k4)
+                umma_tf32_ts_raw(d_lo, a_hi0 + 32 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+            }
+          } else
           if (elect_one()) {
             umma_tf32_ts_raw(d_lo, a_hi0 + 32, desc_of(lb_hi), idesc, acc0);
             umma_tf32_ts_raw(d_lo, a_hi0, desc_of(lb_lo), idesc, 1u);
@@ -502,15 +534,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (++b == p.nl) { b = 0; bph ^= 1u; }
           if (++m == p.nacc) m = 0;
           if (ks + 1 < nk) {
-            mbar_wait(bar_full + 8 * s, sph);           // weights of the next K-step landed
+            mbar_wait(bar_bfull + 8 * s, sph);          // weights of the next K-step landed
             mbar_wait(bar_afull + 8 * b, bph);          // its operand buffer is written
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           if (elect_one()) {
             constexpr int k4 = BK / 8 - 1;
-            umma_tf32_ts_raw(d_lo, a_hi0 + 32 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
-            umma_tf32_ts_raw(d_lo, a_hi0 + k4 * 8, desc_of(lb_lo + 2 * k4), idesc, 1u);
-            umma_tf32_ts_raw(d_main, a_hi0 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+            if (concat) {
+#pragma unroll
+              for (int kk = BK / 16; kk < BK / 8; ++kk)
+                umma_tf32_ts_raw(d_lo, a_hi0 + 32 + kk * 8, desc_of(lb_hi + 2 * kk), idesc, 1u);
+            } else {
+              umma_tf32_ts_raw(d_lo, a_hi0 + 32 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+              umma_tf32_ts_raw(d_lo, a_hi0 + k4 * 8, desc_of(lb_lo + 2 * k4), idesc, 1u);
+              umma_tf32_ts_raw(d_main, a_hi0 + k4 * 8, desc_of(lb_hi + 2 * k4), idesc, 1u);
+            }
             umma_commit_raw(bar_e);        // weights of this stage consumed
             umma_commit_raw(bar_ae);       // operand buffer consumed
           }
@@ -521,12 +559,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       for (int ks = 0; ks < nk; ++ks) {
         const uint32_t d_main = d_base + (uint32_t)(m * BN);
         const bool fresh_main = ks < p.nacc;           // first use of this main accumulator: overwrite
-        mbar_wait(bar_full + 8 * s, sph);             // weights landed
+        mbar_wait(bar_bfull + 8 * s, sph);            // weights landed
         mbar_wait(bar_afull + 8 * b, bph);            // operand buffer b written
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint32_t sbm = b_ring + s * b_slot_bytes;
         const uint32_t a_hi0 = tmem_base + acc_cols + (uint32_t)(b * A_BUF_COLS);
-        const uint32_t lb_hi = desc_lo(sa + A_TILE_BYTES), lb_lo = desc_lo(sa + A_TILE_BYTES + b_tile_bytes);
+        const uint32_t lb_hi = desc_lo(sbm), lb_lo = desc_lo(sbm + b_tile_bytes);
         if (elect_one()) {
 #pragma unroll
           for (int k4 = 0; k4 < BK / 8; ++k4) {
@@ -539,7 +577,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               umma_tf32_ts_raw(d_main, a_hi, desc_of(lb_hi + 2 * k4), idesc, acc_m);
             }
           }
-          umma_commit_raw(bar_empty + 8 * s);      // weights of stage s consumed by this stream
+          umma_commit_raw(bar_bempty + 8 * s);     // weights of slot s consumed by this stream
           umma_commit_raw(bar_aempty + 8 * b);     // operand buffer b consumed by this stream
         }
         __syncwarp();
@@ -554,18 +592,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                  // GEMM row = TMEM lane = pixel within the tile
     // ===== operand converter: group cg owns K-steps cg, cg + GROUPS, ... (= operand buffer cg when GROUPS == 2) =====
-    int s = cg, b = cg;                           // stages >= 2 and nl >= 2 >= GROUPS
+    int s = cg, b = cg;                           // stages_a >= 2 and nl >= 2 >= GROUPS
     uint32_t sph = 0, bph = 0;
     for (int ks = cg; ks < nk; ks += GROUPS) {
       mbar_wait(bar_full + 8 * s, sph);
       const bool tr = p.dbg && threadIdx.x == 64 && ks >= 8 && ks < 14;
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 0] = clock64();
-      const uint8_t* row = smem_gen + (size_t)s * stage_bytes + (size_t)r * 128;
+      const uint8_t* row = smem_gen + (size_t)s * A_TILE_BYTES + (size_t)r * 128;
       uint32_t hi[32], lo[32];
-      const bool skip_lds = (p.dev_flags & 1024) != 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {               // 16-byte chunk j of this row sits at chunk (j ^ (r & 7))
-        const float4 v = skip_lds ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+        const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
         const float a[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -583,16 +620,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 2] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)(b * A_BUF_COLS);
-      if (!(p.dev_flags & 256)) {
-        tmem_st32(ta, hi);
-        tmem_st32(ta + 32, lo);
-      }
+      tmem_st32(ta, hi);
+      tmem_st32(ta + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_afull + 8 * b);
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 3] = clock64();
-      s += GROUPS; if (s >= p.stages) { s -= p.stages; sph ^= 1u; }
+      s += GROUPS; if (s >= p.stages_a) { s -= p.stages_a; sph ^= 1u; }
       b += GROUPS; if (b >= p.nl) { b -= p.nl; bph ^= 1u; }
     }
     // ===== epilogue =====
@@ -1047,21 +1082,27 @@ int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, in
   int n_issue = ((g_dev_flags & 8) && 4 * p.Cout_pad <= tmem_budget) ? 2 : 1;
   int nm = tmem_budget / (n_issue * p.Cout_pad) - 1;
   if (nm > 4) nm = 4;
+  if (nm > 1 && n_issue == 1 && !(g_dev_flags & 4096)) nm = 1;     // one main accumulator: the two-MMA (concatenated) K-slice form
   if (nm < 1) { nrgbd_set_error("conv_tc2: Cout too large for the TMEM operand buffers"); return NRGBD_ERR_UNSUPPORTED; }
   if (g_force_nacc > 0 && g_force_nacc < nm) nm = g_force_nacc;
   p.n_issue = n_issue; p.nacc = nm; p.nl = nbuf;
   int cols = 32; while (cols < n_issue * (nm + 1) * p.Cout_pad + nbuf * A_BUF_COLS) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t stage = (size_t)A_TILE_BYTES + 2 * (size_t)p.Cout_pad * BK * 4;
-  int stages = two_per_sm ? 3 : (int)((220 * 1024 - 2048) / stage);
-  if (stages > 4) stages = 4;
-  if (g_force_stages > 0 && g_force_stages < stages) stages = g_force_stages;
+  // Ring depths (see the kernel): the weight ring gets everything the activation ring leaves. Budget per CTA:
+  // the 227 KB opt-in maximum, or half of the SM's 228 KB minus the 1 KB per-CTA reservation for two CTAs.
+  const size_t b_slot = 2 * (size_t)p.Cout_pad * BK * 4;
+  const size_t budget = (two_per_sm ? 115712 : 232448) - 512;          // 512 bytes of barriers
+  int stages_a = 4, stages = (int)((budget - 4 * (size_t)A_TILE_BYTES) / b_slot);
+  if (stages < 5) { stages_a = 3; stages = (int)((budget - 3 * (size_t)A_TILE_BYTES) / b_slot); }
+  if (stages > 8) stages = 8;
+  if (g_force_stages > 0 && g_force_stages < stages) { stages = g_force_stages; if (stages_a > stages) stages_a = stages; }
   p.dev_flags = g_dev_flags; p.dbg = g_dbg;
   if (stages < 2) { nrgbd_set_error("conv_tc2: Cout too large for the shared-memory pipeline"); return NRGBD_ERR_UNSUPPORTED; }
-  p.stages = stages;
-  size_t ep_bytes = (size_t)((p.Cout_pad + 31) / 32) * 16384;     // output staging slabs alias the pipeline stages
-  size_t smem = (size_t)stages * stage + 1024 + 256;
-  if (stages * stage < ep_bytes) smem = ep_bytes + 1024 + 256;
+  p.stages = stages; p.stages_a = stages_a;
+  size_t ring = (size_t)stages_a * A_TILE_BYTES + (size_t)stages * b_slot;
+  const size_t ep_bytes = (size_t)((p.Cout_pad + 31) / 32) * 16384;    // output staging slabs alias the rings
+  if (ring < ep_bytes) ring = ep_bytes;
+  const size_t smem = ring + 512;
   // TMA tensor store of the output tile: stride-1 outputs whose channel window starts on a 16-byte boundary
   CUtensorMap ty = ta;
   p.tma_store = 0;

@@ -19,7 +19,7 @@ grid = N * (H // 8) * (W // 16)
 dbg = torch.zeros((grid, 64), device=dev, dtype=torch.int64)
 impl = sys.argv[3] if len(sys.argv) > 3 else 'v1'
 flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-L.nrgbd_conv_tc_set_dev(0, flags)
+L.nrgbd_conv_tc_set_dev(int(sys.argv[5]) if len(sys.argv) > 5 else 0, flags)
 def run():
     if impl == 'v2':
         check(L.nrgbd_conv_nhwc_tc2(ptr(x), N, 1, H, W, Cin, Cin, ptr(wh), ptr(wl), None, Cout, Cout, 1, k, k, 1, 1, 1, ptr(y), H, W, Cout, 0, 0,
@@ -51,10 +51,10 @@ for s in np.unique(sm):
 print('  CTAs per SM', np.bincount(sm.astype(int)).max(), 'median gap between CTAs on an SM', np.median(gaps))
 
 if impl == 'v2':
-    # K-step trace of one converter thread (group 0) and the MMA issue lane, K-steps 8..13, relative to
-    # the converter's "raw tile landed" stamp of K-step 8; median over CTAs
+    # K-step trace of the TMA lane, one converter thread (group 0) and the MMA issue lane, K-steps 8..13,
+    # relative to the converter's "raw tile landed" stamp of K-step 8; median over CTAs
     base = d[:, 16:17]
-    tr = np.median(d[:, 16:64].reshape(-1, 6, 8)[:, :, :6] - base[:, None, :], 0)
-    print('  ks   cvt:full  cvt:math  cvt:aempty  cvt:sttm+arrive | mma:afull  mma:issued')
+    tr = np.median(d[:, 16:64].reshape(-1, 6, 8) - base[:, None, :], 0)
+    print('  ks | tma:A-issue tma:B-issue | cvt:landed  cvt:math  cvt:aempty  cvt:sttm+arrive | mma:start  mma:issued')
     for i in range(6):
-        print('  %2d  %9.0f %9.0f %11.0f %16.0f | %9.0f %11.0f' % ((8 + i,) + tuple(tr[i])))
+        print('  %2d | %10.0f %11.0f | %10.0f %9.0f %11.0f %16.0f | %9.0f %11.0f' % ((8 + i, tr[i][6], tr[i][7]) + tuple(tr[i][:6])))
