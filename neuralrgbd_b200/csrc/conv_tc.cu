@@ -613,8 +613,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           hi[j * 4 + k] = hb; lo[j * 4 + k] = __float_as_uint(a[k] - __uint_as_float(hb));
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);                        // this warp is done with the raw tile
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 1] = clock64();
       mbar_wait(bar_aempty + 8 * b, bph ^ 1u);      // MMAs that read buffer b have retired
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 2] = clock64();
@@ -625,7 +623,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_afull + 8 * b);
+      // The raw tile is released only here, after the tcgen05.st that consumed hi / lo: the conversions are
+      // register-only work the compiler is free to sink below an earlier arrive, which would leave the
+      // shared-memory loads outstanding while TMA already refills the slot (seen as rare corrupt rows on
+      // large images once the activation ring had its own, early, release).
+      if (lane == 0) { mbar_arrive(bar_empty + 8 * s); mbar_arrive(bar_afull + 8 * b); }
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 3] = clock64();
       s += GROUPS; if (s >= p.stages_a) { s -= p.stages_a; sph ^= 1u; }
       b += GROUPS; if (b >= p.nl) { b -= p.nl; bph ^= 1u; }

@@ -102,3 +102,20 @@ def test_tc_matches_fp32_simt_path():
     assert rel_err(b, a) <= 6e-6
     c = convops.conv_tc(T(x), T(w), None, 1, 1, 1, impl='v2').cpu().numpy()
     assert rel_err(c, a) <= 6e-6
+
+
+@pytest.mark.parametrize('shape', [(1, 64, 480, 640, 64), (1, 96, 240, 320, 96), (5, 128, 120, 160, 128)])
+def test_tc2_large_images_repeatable(shape):
+    """Many waves of CTAs on HBM-resident inputs: the shared-memory rings and TMEM operand buffers are recycled
+    hundreds of times per SM with irregular TMA latencies. A slot released before its readers had finished
+    showed up only here (a few corrupt tiles per launch), never on the small oracle-sized cases."""
+    from neuralrgbd_b200 import convops
+    n, cin, h, w_, cout = shape
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.randn((n, cin, h, w_), device='cuda', generator=g)
+    w = torch.randn((cout, cin, 3, 3), device='cuda', generator=g) / math.sqrt(cin * 9)
+    ref = convops.conv(x, w, None, 1, 1, 1)
+    scale = float(ref.abs().max())
+    for _ in range(3):
+        y = convops.conv_tc(x, w, None, 1, 1, 1, impl='v2')
+        assert float((y - ref).abs().max()) <= 1e-5 * scale
