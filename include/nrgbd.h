@@ -29,6 +29,7 @@ typedef struct CUstream_st* nrgbd_stream_t;
 #define NRGBD_ERR_CUDA (-2)
 #define NRGBD_ERR_UNSUPPORTED (-3)
 #define NRGBD_ERR_NOMEM (-4)
+#define NRGBD_ERR_IO (-5)
 
 #define NRGBD_METRIC_L2 0 /* img_dis_L2_pard, warping/homography.py:81-83 */
 #define NRGBD_METRIC_L1 1 /* img_dis_L1_pard, warping/homography.py:85-87 */
@@ -108,6 +109,22 @@ int nrgbd_depth_regression(const float* bv, int n_pix, int D, long long in_sd, l
                            const float* d_planes, int bv_log, float* depth, float* conf,
                            nrgbd_stream_t stream);
 int nrgbd_exp(const float* x, long long n, float* y, nrgbd_stream_t stream);
+
+/* ---- f-2: output stage (replaces test_utils/export_res.py:37-75 export_res_img and the map part of
+ * :77-100 export_res_refineNet, which move the whole D x H x W volume to the host first) -----------
+ * One pass over the reference-layout log-DPV [D][HW] (plane-major, device):
+ *   dmap[p] = sum_d exp(bv[d][p]) * d_candi[d]   (depth_regression :37-41; misc.depth_val_regression)
+ *   conf[p] = exp(max_d bv[d][p])                (:56-59)
+ *   dmap_u16 = (uint16)(dmap * depth_scale), conf_u16 = (uint16)(conf * conf_scale)   (:74-75, numpy
+ *   astype(np.uint16): truncation toward zero; out-of-range values, undefined there, are clamped)
+ * Any of the four outputs may be NULL. d_candi: device float[D]. */
+int nrgbd_export_depth_conf(const float* log_dpv, const float* d_candi, int D, long long HW, float depth_scale,
+                            float conf_scale, float* dmap, float* conf, unsigned short* dmap_u16,
+                            unsigned short* conf_u16, nrgbd_stream_t stream);
+/* Host-only: 16-bit binary PGM byte-identical to mio/imgIO.py:9-10 export2pgm (PIL mode 'I' -> P5,
+ * maxval 65535, big-endian samples). pixels: HOST pointer, row-major [height][width].
+ * Returns 0, NRGBD_ERR_BAD_ARG, or NRGBD_ERR_IO when the file cannot be written. */
+int nrgbd_write_pgm16(const char* path, const unsigned short* pixels, int width, int height);
 
 /* ---- a5, a8, a10: conv stacks (channels-last fp32, channel stride Cs % 4 == 0) ---------------
  * Replace nn.Conv2d/Conv3d/ConvTranspose2d (+bias, +LeakyReLU) and training-mode BatchNorm

@@ -140,3 +140,21 @@ def stats(a):
     a = np.asarray(a, np.float64)
     fin = np.isfinite(a)
     return np.array([a[fin].sum(), np.square(a[fin]).sum(), float(fin.sum())], np.float64)
+
+
+# ---- output stage: a refined log-DPV, its plane depths and the (normalised) reference image --------
+def export_case(name):
+    """-> bv [1, D, H, W] float32 log-probabilities, d_candi float64 [D], img [1, 3, H, W] float32."""
+    cfg = {'export_48x64_d16': dict(D=16, H=48, W=64, lo=0.1, hi=5.0, sharp=3.0, seed=31),
+           'export_ragged_37x53_d64': dict(D=64, H=37, W=53, lo=0.1, hi=5.0, sharp=6.0, seed=32),
+           'export_kitti_d128': dict(D=128, H=24, W=80, lo=1.0, hi=60.0, sharp=2.0, seed=33)}[name]
+    rng = np.random.RandomState(cfg['seed'])
+    z = (rng.standard_normal((1, cfg['D'], cfg['H'], cfg['W'])) * cfg['sharp']).astype(np.float32)
+    z = z - z.max(axis=1, keepdims=True)
+    bv = (z - np.log(np.exp(z.astype(np.float64)).sum(axis=1, keepdims=True))).astype(np.float32)
+    d_candi = np.linspace(cfg['lo'], cfg['hi'], cfg['D'])
+    img = rng.standard_normal((1, 3, cfg['H'], cfg['W'])).astype(np.float32)
+    return bv, d_candi, img
+
+
+EXPORT_CASES = ['export_48x64_d16', 'export_ragged_37x53_d64', 'export_kitti_d128']
