@@ -110,6 +110,21 @@ int nrgbd_depth_regression(const float* bv, int n_pix, int D, long long in_sd, l
                            nrgbd_stream_t stream);
 int nrgbd_exp(const float* x, long long n, float* y, nrgbd_stream_t stream);
 
+/* ---- f-1: backward of the plane sweep (autograd of warping/homography.py:293-331 as used by
+ * train_utils/train_KVNet.py:149-153; R, t, K, d are constants: only the two feature gradients) ----------------
+ * Same packed layout, camera terms and workspace as nrgbd_plane_sweep_cost_packed. grad_cost_hwd [h*w][D].
+ * g_ref_* / g_src_* have the shapes of ref_* / src_*; g_src_* are zeroed by the call, then scatter-added with
+ * vector atomics (order not deterministic, like ATen's grid_sampler backward). */
+int nrgbd_plane_sweep_backward_packed(const float* ref_wide, const float* ref_narrow, const float* src_wide,
+                                      const float* src_narrow, int Cw, int Cn, int V, int D, int h, int w,
+                                      const float* K, const float* R, const float* t, const float* rays,
+                                      const float* d_planes, float cx, float cy, float sigma, int metric, float* ws,
+                                      const float* grad_cost_hwd, float* g_ref_wide, float* g_ref_narrow,
+                                      float* g_src_wide, float* g_src_narrow, nrgbd_stream_t stream);
+/* Inverse of nrgbd_pack_features: n_img images of wide [hw][C - C%4] (+ narrow [hw][4]) -> NCHW [C][hw]. */
+int nrgbd_unpack_features(const float* wide, const float* narrow, int C, int hw, int n_img, float* nchw,
+                          nrgbd_stream_t stream);
+
 /* ---- f-2: output stage (replaces test_utils/export_res.py:37-75 export_res_img and the map part of
  * :77-100 export_res_refineNet, which move the whole D x H x W volume to the host first) -----------
  * One pass over the reference-layout log-DPV [D][HW] (plane-major, device):

@@ -90,6 +90,67 @@ def pack_features(x_nchw):
     return wide, narrow
 
 
+def unpack_features(wide, narrow, C, h, w):
+    """Inverse of pack_features: (wide [N,hw,Cw], narrow [N,hw,4]) -> [N,C,h,w]."""
+    L = _lib.lib()
+    t0 = wide if wide is not None else narrow
+    N = t0.shape[0]
+    out = torch.empty((N, C, h, w), device=t0.device, dtype=torch.float32)
+    check(L.nrgbd_unpack_features(ptr(wide), ptr(narrow), C, h * w, N, ptr(out), _stream()))
+    return out
+
+
+def _sweep_forward(ref_w, ref_n, src_w, src_n, C, V, D, H, W, K, Rs, ts, rays, dpl, cx, cy, sigma, metric):
+    L = _lib.lib()
+    dev = (ref_w if ref_w is not None else ref_n).device
+    ws = torch.empty(L.nrgbd_sweep_workspace_floats(V), device=dev, dtype=torch.float32)
+    cost_hwd = torch.empty((H * W, D), device=dev, dtype=torch.float32)
+    check(L.nrgbd_plane_sweep_cost_packed(ptr(ref_w), ptr(ref_n), ptr(src_w), ptr(src_n), C - C % 4, C % 4,
+                                          V, D, H, W, ptr(K), ptr(Rs), ptr(ts), ptr(rays), ptr(dpl),
+                                          _F(cx), _F(cy), _F(sigma), metric, ptr(ws), ptr(cost_hwd), _stream()))
+    costV = torch.empty((1, D, H, W), device=dev, dtype=torch.float32)
+    check(L.nrgbd_transpose2d(ptr(cost_hwd), H * W, D, ptr(costV), _stream()))
+    return costV
+
+
+class _PlaneSweepCost(torch.autograd.Function):
+    """est_swp_volume_v4 with the feature gradients the reference gets from autograd
+    (train_utils/train_KVNet.py:149-153); poses, intrinsics and plane depths carry no gradient there either."""
+
+    @staticmethod
+    def forward(ctx, feat_img_ref, feat_img_src, K, Rs, ts, rays, dpl, cx, cy, sigma, metric):
+        C, H, W = feat_img_ref.shape[1:]
+        V, D = feat_img_src.shape[1], dpl.numel()
+        ref_w, ref_n = pack_features(feat_img_ref.detach().float())
+        src_w, src_n = pack_features(feat_img_src.detach()[0].float())
+        ctx.save_for_backward(*[x if x is not None else torch.empty(0, device=K.device) for x in (ref_w, ref_n, src_w, src_n)],
+                              K, Rs, ts, rays, dpl)
+        ctx.meta = (C, V, D, H, W, cx, cy, sigma, metric)
+        return _sweep_forward(ref_w, ref_n, src_w, src_n, C, V, D, H, W, K, Rs, ts, rays, dpl, cx, cy, sigma, metric)
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        L = _lib.lib()
+        ref_w, ref_n, src_w, src_n, K, Rs, ts, rays, dpl = ctx.saved_tensors
+        C, V, D, H, W, cx, cy, sigma, metric = ctx.meta
+        opt = lambda x: x if x.numel() else None          # noqa: E731
+        ref_w, ref_n, src_w, src_n = opt(ref_w), opt(ref_n), opt(src_w), opt(src_n)
+        dev = K.device
+        with torch.cuda.device(dev):
+            g_hwd = torch.empty((H * W, D), device=dev, dtype=torch.float32)
+            check(L.nrgbd_transpose2d(ptr(grad_cost.detach().float().contiguous()), D, H * W, ptr(g_hwd), _stream()))
+            like = lambda x: torch.empty_like(x) if x is not None else None      # noqa: E731
+            g_rw, g_rn, g_sw, g_sn = like(ref_w), like(ref_n), like(src_w), like(src_n)
+            ws = torch.empty(L.nrgbd_sweep_workspace_floats(V), device=dev, dtype=torch.float32)
+            check(L.nrgbd_plane_sweep_backward_packed(ptr(ref_w), ptr(ref_n), ptr(src_w), ptr(src_n), C - C % 4, C % 4, V, D, H, W,
+                                                      ptr(K), ptr(Rs), ptr(ts), ptr(rays), ptr(dpl), _F(cx), _F(cy), _F(sigma),
+                                                      metric, ptr(ws), ptr(g_hwd), ptr(g_rw), ptr(g_rn), ptr(g_sw), ptr(g_sn),
+                                                      _stream()))
+            g_ref = unpack_features(g_rw, g_rn, C, H, W)
+            g_src = unpack_features(g_sw, g_sn, C, H, W).unsqueeze(0)
+        return g_ref, g_src, None, None, None, None, None, None, None, None, None
+
+
 def est_swp_volume_v4(feat_img_ref, feat_img_src, d_candi, R, t, cam_intrinsic, costV_sigma,
                       feat_dist='L2', debug_ipdb=False):
     r'''
@@ -97,31 +158,25 @@ def est_swp_volume_v4(feat_img_ref, feat_img_src, d_candi, R, t, cam_intrinsic, 
     feat_img_src - NVCHW tensor.  V is for different views
     R, t - R[idx_view, :, :] - 3x3 rotation matrix
            t[idx_view, :] - 3x1 transition vector
-    Returns costV [1, D, H, W] (homography.py:293-331).
+    Returns costV [1, D, H, W] (homography.py:293-331). Differentiable w.r.t. the two feature tensors
+    (the reference trains through it, train_utils/train_KVNet.py:149-153).
     '''
     if feat_dist not in ('L2', 'L1'):
         raise Exception('undefined metric for feature distance ...')
-    L = _lib.lib()
     dev = _dev(feat_img_ref)
     with torch.cuda.device(dev):
-        H, W, D = feat_img_ref.shape[2], feat_img_ref.shape[3], len(d_candi)
-        C = feat_img_ref.shape[1]
-        V = feat_img_src.shape[1]
         K, rays = _cam_tensors(cam_intrinsic, dev)
         dpl = _planes(d_candi, dev)
         Rs, ts = _stack_Rt(R, t, dev)
+        cx = float(cam_intrinsic['intrinsic_M'][0, 2]); cy = float(cam_intrinsic['intrinsic_M'][1, 2])
+        metric = 0 if feat_dist == 'L2' else 1
+        if torch.is_grad_enabled() and (feat_img_ref.requires_grad or feat_img_src.requires_grad):
+            return _PlaneSweepCost.apply(feat_img_ref, feat_img_src, K, Rs, ts, rays, dpl, cx, cy, float(costV_sigma), metric)
+        C, H, W = feat_img_ref.shape[1:]
         ref_w, ref_n = pack_features(feat_img_ref.float())
         src_w, src_n = pack_features(feat_img_src[0].float())
-        cx = float(cam_intrinsic['intrinsic_M'][0, 2]); cy = float(cam_intrinsic['intrinsic_M'][1, 2])
-        ws = torch.empty(L.nrgbd_sweep_workspace_floats(V), device=dev, dtype=torch.float32)
-        cost_hwd = torch.empty((H * W, D), device=dev, dtype=torch.float32)
-        check(L.nrgbd_plane_sweep_cost_packed(ptr(ref_w), ptr(ref_n), ptr(src_w), ptr(src_n), C - C % 4, C % 4,
-                                              V, D, H, W, ptr(K), ptr(Rs), ptr(ts), ptr(rays), ptr(dpl),
-                                              _F(cx), _F(cy), _F(float(costV_sigma)),
-                                              0 if feat_dist == 'L2' else 1, ptr(ws), ptr(cost_hwd), _stream()))
-        costV = torch.empty((1, D, H, W), device=dev, dtype=torch.float32)
-        check(L.nrgbd_transpose2d(ptr(cost_hwd), H * W, D, ptr(costV), _stream()))
-    return costV
+        return _sweep_forward(ref_w, ref_n, src_w, src_n, C, feat_img_src.shape[1], len(d_candi), H, W, K, Rs, ts, rays, dpl,
+                              cx, cy, float(costV_sigma), metric)
 
 
 def _warp_views(feat_img_src, d_candi, R, t, K, rays, cx, cy):

@@ -387,3 +387,63 @@ def valid_dpv(dpv_in):
     if a.ndim not in (2, 3, 4, 5):
         raise Exception('wrong dimension for input dpv !')
     return not bool(np.isnan(a.reshape(-1)[0]))
+
+
+# --------------------------------------------------------------------------
+# f-1: backward of the plane-sweep cost volume (what autograd does to
+# est_swp_volume_v4 in train_utils/train_KVNet.py:149-153: grid_sample backward =
+# scatter-add of the bilinear weights, then the distance; R, t, d, K are constants)
+# --------------------------------------------------------------------------
+def _corners(gx, gy, W, H):
+    """Corner indices / validity / weights of grid_sample_2d_zeros for grids of any shape."""
+    ix = _unnormalize(gx.astype(f32), W)
+    iy = _unnormalize(gy.astype(f32), H)
+    x0f = np.floor(ix); y0f = np.floor(iy)
+    x1f = x0f + f32(1); y1f = y0f + f32(1)
+    ws = [(x1f - ix) * (y1f - iy), (ix - x0f) * (y1f - iy), (x1f - ix) * (iy - y0f), (ix - x0f) * (iy - y0f)]
+    bad = ~np.isfinite(ix) | ~np.isfinite(iy) | (np.abs(ix) > 1e9) | (np.abs(iy) > 1e9)
+    x0 = np.where(bad, -10, x0f).astype(np.int64); y0 = np.where(bad, -10, y0f).astype(np.int64)
+    out = []
+    for (xx, yy), wgt in zip(((x0, y0), (x0 + 1, y0), (x0, y0 + 1), (x0 + 1, y0 + 1)), ws):
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H) & ~bad
+        out.append((np.where(ok, yy * W + xx, 0), np.where(ok, wgt, f32(0)).astype(f32)))
+    return out
+
+
+def est_swp_volume_v4_backward(grad_cost, feat_img_ref, feat_img_src, d_candi, R, t, cam_intrinsic,
+                               costV_sigma, feat_dist='L2'):
+    """Gradients of est_swp_volume_v4 w.r.t. feat_img_ref [1,C,h,w] and feat_img_src [1,V,C,h,w]
+    for grad_cost [1,D,h,w]. Accumulated in float64 (the device scatter has no defined order)."""
+    if feat_dist not in ('L2', 'L1'):
+        raise Exception('undefined metric for feature distance ...')
+    ref = np.asarray(feat_img_ref, f32)[0]
+    src = np.asarray(feat_img_src, f32)[0]
+    g = np.asarray(grad_cost, np.float64)[0]
+    C, h, w = ref.shape
+    V = src.shape[0]
+    d32 = np.asarray(d_candi).astype(f32)
+    D = len(d32)
+    K = cam_intrinsic['intrinsic_M_cuda']
+    rays = cam_intrinsic['unit_ray_array_2D']
+    cx, cy = cam_intrinsic['intrinsic_M'][0, 2], cam_intrinsic['intrinsic_M'][1, 2]
+    gref = np.zeros((C, h * w), np.float64)
+    gsrc = np.zeros((V, C, h * w), np.float64)
+    sigma = float(f32(costV_sigma))
+    for v in range(V):
+        term1, _, term2 = homography_terms(K, R[v], t[v], rays)
+        gx, gy = back_warp_grid(term1, term2, d32, cx, cy)
+        flat = src[v].reshape(C, h * w)
+        for d in range(D):
+            cor = _corners(gx[d].reshape(h, w), gy[d].reshape(h, w), w, h)
+            s = np.zeros((C, h, w), f32)
+            for idx, wgt in cor:
+                s = s + flat[:, idx.reshape(-1)].reshape(C, h, w) * wgt[None]
+            diff = (s - ref).astype(np.float64)
+            dphi = 2.0 * diff if feat_dist == 'L2' else np.sign(diff)
+            gs = dphi * (g[d] / sigma)[None]                 # dLoss/dS  [C,h,w]
+            gref -= gs.reshape(C, -1)
+            for idx, wgt in cor:
+                contrib = (gs * wgt[None].astype(np.float64)).reshape(C, -1)
+                for c in range(C):
+                    np.add.at(gsrc[v, c], idx.reshape(-1), contrib[c])
+    return gref.reshape(1, C, h, w).astype(f32), gsrc.reshape(1, V, C, h, w).astype(f32)

@@ -40,6 +40,8 @@ def sweep_case(name):
         'c1_320x256_v1_d32_c3': dict(seed=12, h=256, w=320, C=3, V=1, D=32, dist='L2'),
         'small_v4_d32_c67_L2': dict(seed=13, h=64, w=80, C=67, V=4, D=32, dist='L2'),
         'small_v4_d32_c67_L1': dict(seed=13, h=64, w=80, C=67, V=4, D=32, dist='L1'),
+        'bwd_v2_d8_c67_L2': dict(seed=17, h=40, w=56, C=67, V=2, D=8, dist='L2'),
+        'bwd_v2_d8_c67_L1': dict(seed=17, h=40, w=56, C=67, V=2, D=8, dist='L1'),
         'ragged_v3_d7_c5': dict(seed=14, h=37, w=53, C=5, V=3, D=7, dist='L2'),
         # d_min = 0 plane (test_KVNet.py:58 default) and a camera moved *behind* the
         # reference so that P_z <= 0 for near planes (the +1e-10 path, homography.py:438)
@@ -59,6 +61,18 @@ def sweep_case(name):
     return dict(ref=ref, src=src, d=d, R=np.ascontiguousarray(poses[:, :3, :3]),
                 t=np.ascontiguousarray(poses[:, :3, 3]), w=cfg['w'], h=cfg['h'], sigma=10.0,
                 feat_dist=cfg['dist'])
+
+
+# small enough for torch autograd through the reference's D x C x h x w intermediates on CPU
+SWEEP_BACKWARD_CASES = ['bwd_v2_d8_c67_L2', 'bwd_v2_d8_c67_L1', 'ragged_v3_d7_c5', 'dzero_behind_v2_d16_c8']
+
+
+def sweep_grad(name, shape):
+    """Seeded upstream gradient d loss / d cost [1, D, h, w] (with a block of exact zeros: skipped planes)."""
+    rng = np.random.RandomState(sum(name.encode()) % 10007)
+    g = rng.standard_normal(shape).astype(np.float32)
+    g[:, ::3, : shape[2] // 4] = 0.0
+    return g
 
 
 SWEEP_CASES = ['c1_320x256_v1_d32_c67', 'c1_320x256_v1_d32_c3', 'small_v4_d32_c67_L2',
