@@ -85,6 +85,28 @@ def main():
                                      F(h / 2), ptr(ws), ptr(outw), st()))
     med, mn = timeit(warp)
     res['warp_to_volume'] = dict(us_med=med, us_min=mn, GBps=V * (3 * hw + 3 * D * hw) * 4 / med / 1e3)
+    # f-1: sweep backward (scatter of the four bilinear weights with 16-byte vector atomics)
+    gcost = torch.randn(hw, D, device=dev)
+    g_rw = torch.empty_like(ref_w); g_rn = torch.empty_like(ref_n); g_sw = torch.empty_like(src_w); g_sn = torch.empty_like(src_n)
+
+    def bwd():
+        check(L.nrgbd_plane_sweep_backward_packed(ptr(ref_w), ptr(ref_n), ptr(src_w), ptr(src_n), Cw, Cn, V, D, h, w, ptr(K), ptr(R), ptr(t),
+                                                  ptr(rays), ptr(dpl), F(w / 2), F(h / 2), F(10.), 0, ptr(ws), ptr(gcost), ptr(g_rw), ptr(g_rn),
+                                                  ptr(g_sw), ptr(g_sn), st()))
+    med, mn = timeit(bwd)
+    n_red = V * D * hw * 4 * (Cw // 4 + (1 if Cn else 0))
+    res['sweep_backward'] = dict(us_med=med, us_min=mn, vector_atomics=n_red, atomics_per_ns=n_red / med / 1e3,
+                                 alg_MB=(2 * (1 + V) * C * hw * 4 + D * hw * 4) / 1e6)
+    # f-2: output stage at full resolution (640x480 when the sweep shape is 120x160)
+    HW = 16 * hw
+    bvf = torch.log_softmax(torch.randn(D, HW, device=dev), 0).contiguous()
+    dm = torch.empty(HW, device=dev); cf = torch.empty(HW, device=dev)
+    d16 = torch.empty(HW, device=dev, dtype=torch.int16); c16 = torch.empty(HW, device=dev, dtype=torch.int16)
+
+    def export():
+        check(L.nrgbd_export_depth_conf(ptr(bvf), ptr(dpl), D, HW, F(1000.), F(1000.), ptr(dm), ptr(cf), ptr(d16), ptr(c16), st()))
+    med, mn = timeit(export)
+    res['export_depth_conf'] = dict(us_med=med, us_min=mn, alg_MB=(D * HW * 4 + 12 * HW) / 1e6, GBps=(D * HW * 4 + 12 * HW) / med / 1e3)
     print(json.dumps(dict(shape=dict(h=h, w=w, C=C, V=V, D=D), kernels=res), indent=1))
 
 
