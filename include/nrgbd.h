@@ -125,6 +125,14 @@ int nrgbd_plane_sweep_backward_packed(const float* ref_wide, const float* ref_na
 int nrgbd_unpack_features(const float* wide, const float* narrow, int C, int hw, int n_img, float* nchw,
                           nrgbd_stream_t stream);
 
+/* ---- f-4: input stage (replaces mdataloader/scanNet.py:368-369 PIL nearest resize and
+ * mdataloader/m_preprocess.py:15-21 ToTensor + Normalize, both host-side per frame) ------------------------------
+ * dst[c][y][x] = ((float)src[ys[y]][xs[x]][c] / 255 - mean[c]) / std[c], each op rounded in fp32 (bit-exact with
+ * torchvision). src_hwc: device uint8 [Hs][Ws][3]; ys [H], xs [W]: device int32 source indices (PIL's NEAREST table,
+ * neuralrgbd_b200.mdataloader.m_preprocess.nearest_index); mean3 / std3: HOST float[3]; dst_chw: device [3][H][W]. */
+int nrgbd_preprocess_rgb_u8(const unsigned char* src_hwc, int Hs, int Ws, const int* ys, const int* xs, int H, int W,
+                            const float* mean3, const float* std3, float* dst_chw, nrgbd_stream_t stream);
+
 /* ---- f-2: output stage (replaces test_utils/export_res.py:37-75 export_res_img and the map part of
  * :77-100 export_res_refineNet, which move the whole D x H x W volume to the host first) -----------
  * One pass over the reference-layout log-DPV [D][HW] (plane-major, device):

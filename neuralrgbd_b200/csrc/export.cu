@@ -32,8 +32,18 @@ export_depth_conf_kernel(const float* __restrict__ bv, const float* __restrict__
   if (p >= HW) return;
   // products are rounded before they are added (exp(BV) * Depth_val_vol is materialised in the reference)
   float acc = 0.f, m = -INFINITY;
-#pragma unroll 4
-  for (int d = 0; d < D; ++d) {
+  int d = 0;
+  for (; d + 8 <= D; d += 8) {                 // eight independent loads in flight per thread (HBM latency)
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(bv + (long long)(d + j) * HW + p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc = __fadd_rn(acc, __fmul_rn(expf(v[j]), dc[d + j]));
+      m = fmaxf(m, v[j]);
+    }
+  }
+  for (; d < D; ++d) {
     const float v = __ldg(bv + (long long)d * HW + p);
     acc = __fadd_rn(acc, __fmul_rn(expf(v), dc[d]));
     m = fmaxf(m, v);

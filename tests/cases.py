@@ -172,3 +172,18 @@ def export_case(name):
 
 
 EXPORT_CASES = ['export_48x64_d16', 'export_ragged_37x53_d64', 'export_kitti_d128']
+
+
+# ---- input stage: decoded uint8 frames and target sizes (W, H) ------------------------------------
+def preprocess_case(name):
+    cfg = {'pre_down_97x131_to_64x48': dict(Hs=97, Ws=131, size=(64, 48), seed=41),
+           'pre_up_37x53_to_80x64': dict(Hs=37, Ws=53, size=(80, 64), seed=42),
+           'pre_same_48x64': dict(Hs=48, Ws=64, size=None, seed=43),
+           'pre_odd_100x100_to_77x33': dict(Hs=100, Ws=100, size=(77, 33), seed=44)}[name]
+    rng = np.random.RandomState(cfg['seed'])
+    img = rng.randint(0, 256, (cfg['Hs'], cfg['Ws'], 3)).astype(np.uint8)
+    img[0, 0] = (0, 0, 0); img[-1, -1] = (255, 255, 255)
+    return img, cfg['size']
+
+
+PREPROCESS_CASES = ['pre_down_97x131_to_64x48', 'pre_up_37x53_to_80x64', 'pre_same_48x64', 'pre_odd_100x100_to_77x33']
