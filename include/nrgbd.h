@@ -186,8 +186,8 @@ int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const
  * identical to nrgbd_conv_nhwc / nrgbd_conv_transpose2d_k4s2_nhwc. */
 int nrgbd_conv_tc_supported(int Cin_pad, int Cout_pad);   /* Cin_pad % 32 == 0, Cout_pad % 16 == 0, <= 256 */
 void nrgbd_conv_tc_set_nacc(int n);  /* development knob: cap on the rotating main accumulators (0 = auto) */
-void nrgbd_conv_tc_set_dev(int stages, int flags); /* development knobs: pipeline depth cap; flags bit0 = plain 1xTF32 */
-void nrgbd_conv_tc_set_debug_buffer(long long* device_buf); /* development: [grid][8] clock64 stamps of the v1 kernel */
+void nrgbd_conv_tc_set_dev(int stages, int flags); /* development knobs: ring depth cap; A/B flags listed in csrc/conv_tc.cu */
+void nrgbd_conv_tc_set_debug_buffer(long long* device_buf); /* development: [grid][64] clock64 stamps (tools/tc_timeline.py) */
 int nrgbd_mma_probe(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, int n_ctas, long long* out,
                     nrgbd_stream_t stream);   /* development: raw tcgen05.mma rate probe */
 int nrgbd_split_tf32(const float* x, long long n, float* hi, float* lo, nrgbd_stream_t stream);
