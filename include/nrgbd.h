@@ -204,6 +204,23 @@ int nrgbd_conv_transpose2d_k4s2_nhwc_tc(const float* x_hi, const float* x_lo, in
                                         int c_off, int leaky, nrgbd_stream_t stream);
 /* v2 tensor-core kernels: raw fp32 activations (the TF32 split happens in-kernel, operand A is fed
  * from TMEM), pre-split K-major weights. Cout_pad <= 128. Same semantics as the v1 entries. */
+/* Training-mode BatchNorm (+ReLU) of a conv's INPUT, folded into the consuming tcgen05 convolution: x is the RAW output
+ * of the producing conv (psm_submodule.convbn :10-16 = Conv2d + BatchNorm2d, BasicBlock :31-49 conv1 -> bn -> relu -> conv2)
+ * and `stats` its per-channel [sum(C) | sum of squares(C)] as written by the conv entry points. The consumer computes
+ * scale = gamma / sqrt(var + eps), shift = beta - mean * scale per CTA and applies fmaf(x, scale, shift) (+ReLU) while it
+ * converts its operands - the same arithmetic as nrgbd_bn_apply_stats, without that pass over the tensor. Padding stays
+ * zero. running_mean / running_var (optional) get the momentum update once. `stats` must differ from the consumer's own. */
+typedef struct nrgbd_bn_input {
+  const double* stats; double count;            /* [2*C] sums of the producing conv; number of positions N*D*H*W */
+  const float* gamma; const float* beta;        /* BatchNorm weight / bias [C] */
+  float* running_mean; float* running_var;      /* optional [C] */
+  float eps, momentum;
+  int relu, C;
+} nrgbd_bn_input;
+int nrgbd_conv_nhwc_tc2_bn_in(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
+                              const float* w_lo, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw,
+                              int stride, int pad, int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off,
+                              int leaky, double* stats, const nrgbd_bn_input* in_bn, nrgbd_stream_t stream);
 int nrgbd_conv_tc2_supported(int Cin_pad, int Cout_pad);
 int nrgbd_conv_nhwc_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in,
                         const float* w_hi, const float* w_lo, const float* bias, int Cout, int Cout_pad,

@@ -220,3 +220,32 @@ def conv_transpose2d_tc(x, w, bias=None, leaky=False, impl='v1'):
         check(L.nrgbd_conv_transpose2d_k4s2_nhwc_tc(ptr(xh), ptr(xl), N, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout,
                                                     Cout_pad, ptr(y), Cs_out, 0, 1 if leaky else 0, _st()))
     return from_cl(y, Cout)
+
+
+def conv_tc_bn_in(x_raw, in_stats, gamma, beta, w, bias=None, stride=1, pad=0, dilation=1, relu=True, leaky=False,
+                  want_stats=False, eps=1e-5, running=None):
+    """conv(relu(batch_norm_train(x_raw))) in one kernel: x_raw [N,C,H,W] is the raw output of the producing conv and
+    in_stats its [2,C] float64 sums (conv(..., want_stats=True)); the normalisation happens in the consumer's operand
+    converter (nrgbd_conv_nhwc_tc2_bn_in). running = (running_mean, running_var) tensors to update, optional."""
+    L = _lib.lib()
+    assert x_raw.dim() == 4
+    N, Cin, Hin, Win = x_raw.shape
+    Cout = w.shape[0]
+    Cin_pad, Cout_pad = pad_to(Cin, 32), pad_to(Cout, 16)
+    xc = to_cl_padded(x_raw, Cin_pad)
+    kh, kw = w.shape[-2], w.shape[-1]
+    Ho = (Hin + 2 * pad - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (Win + 2 * pad - dilation * (kw - 1) - 1) // stride + 1
+    wh, wl = pack_weight_tc(w)
+    Cs_out = pad4(Cout)
+    y = torch.zeros((N, Ho, Wo, Cs_out), device=x_raw.device, dtype=torch.float32)
+    stats = torch.zeros((2, Cout), device=x_raw.device, dtype=torch.float64) if want_stats else None
+    g = gamma.float().contiguous(); b = beta.float().contiguous()
+    d = _lib.BnInput(ctypes.c_void_p(in_stats.data_ptr()), float(N * Hin * Win), ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                     ctypes.c_void_p(running[0].data_ptr()) if running else None, ctypes.c_void_p(running[1].data_ptr()) if running else None,
+                     eps, 0.1, 1 if relu else 0, Cin)
+    check(L.nrgbd_conv_nhwc_tc2_bn_in(ptr(xc), N, 1, Hin, Win, Cin_pad, Cin_pad, ptr(wh), ptr(wl), ptr(bias), Cout, Cout_pad, 1, kh, kw,
+                                      stride, pad, dilation, ptr(y), Ho, Wo, Cs_out, 0, 1 if leaky else 0,
+                                      ctypes.c_void_p(stats.data_ptr()) if want_stats else None, ctypes.byref(d), _st()))
+    out = from_cl(y, Cout)
+    return (out, stats) if want_stats else out

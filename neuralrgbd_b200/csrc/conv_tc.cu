@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "../../include/nrgbd.h"
 
 namespace {
 
@@ -43,6 +44,12 @@ struct TcParams {
   int n_issue;                       // MMA issue streams (warps): 1 or 2
   int tma_store;                     // v2: output tile leaves through a TMA tensor store (stride-1 outputs)
   int stages_a;                      // v2: activation-ring depth (stages = weight-ring depth)
+  // v2, optional: training-mode BatchNorm (+ReLU) of the INPUT tensor applied in the converter (the producing conv
+  // left raw outputs + per-channel sums): x' = [relu](x * scale[c] + shift[c]), zero outside the image
+  const double* in_stats; double in_count;
+  const float* in_gamma; const float* in_beta; float* in_run_mean; float* in_run_var;
+  float in_eps, in_momentum;
+  int in_relu, in_C, in_H, in_W, in_D;
   long long* dbg;                    // optional [grid][64] clock64 timestamps (development)
   signed char dz[MAX_TAPS_TC], dy[MAX_TAPS_TC], dx[MAX_TAPS_TC];
   unsigned char wsel[MAX_TAPS_TC];
@@ -416,6 +423,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_bfull = bars + 128, bar_bempty = bars + 192,
                  bar_afull = bars + 256, bar_aempty = bars + 288, bar_tmem = bars + 320;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + ring_bytes + 328);
+  float* in_sc = reinterpret_cast<float*>(smem_gen + ring_bytes + 512);        // [Cin_pad] scale, then [Cin_pad] shift
+  const int cin_pad = p.cin_chunks * BK;
+  float* in_sh = in_sc + cin_pad;
 
   const long long t_start = clock64();
   const int warp = uniform_warp_idx(), lane = threadIdx.x % 32;
@@ -436,6 +446,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_lo) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_y) : "memory");
+  }
+  if (p.in_stats) {
+    // the BatchNorm of the producing layer, finalised per CTA exactly as nrgbd_bn_apply_stats does (conv.cu)
+    for (int c = threadIdx.x; c < cin_pad; c += blockDim.x) {
+      float sc = 0.f, sh = 0.f;
+      if (c < p.in_C) {
+        const double mean = p.in_stats[c] / p.in_count;
+        double var = p.in_stats[p.in_C + c] / p.in_count - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
+        sc = p.in_gamma[c] * invstd;
+        sh = p.in_beta[c] - (float)mean * sc;
+        if (p.in_run_mean && blockIdx.x == 0) {
+          const double unb = p.in_count > 1 ? var * p.in_count / (p.in_count - 1) : var;
+          p.in_run_mean[c] = (1.f - p.in_momentum) * p.in_run_mean[c] + p.in_momentum * (float)mean;
+          p.in_run_var[c] = (1.f - p.in_momentum) * p.in_run_var[c] + p.in_momentum * (float)unb;
+        }
+      }
+      in_sc[c] = sc; in_sh[c] = sh;
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -594,6 +624,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // ===== operand converter: group cg owns K-steps cg, cg + GROUPS, ... (= operand buffer cg when GROUPS == 2) =====
     int s = cg, b = cg;                           // stages_a >= 2 and nl >= 2 >= GROUPS
     uint32_t sph = 0, bph = 0;
+    const bool fuse_in = p.in_stats != nullptr;
+    int f_cc = cg, f_tap = 0;                     // channel chunk / tap of this group's K-step (fused input BN only)
+    while (f_cc >= p.cin_chunks) { f_cc -= p.cin_chunks; ++f_tap; }
+    const int in_py = (oy0 + r / TW) * p.in_stride, in_px = (ox0 + r % TW) * p.in_stride;
     for (int ks = cg; ks < nk; ks += GROUPS) {
       mbar_wait(bar_full + 8 * s, sph);
       const bool tr = p.dbg && threadIdx.x == 64 && ks >= 8 && ks < 14;
@@ -603,7 +637,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {               // 16-byte chunk j of this row sits at chunk (j ^ (r & 7))
         const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
-        const float a[4] = {v.x, v.y, v.z, v.w};
+        float a[4] = {v.x, v.y, v.z, v.w};
+        if (fuse_in) {
+          // y = [relu](x * scale + shift) of the producing layer's BatchNorm, same fmaf as the stand-alone pass;
+          // TMA zero-filled the padding with RAW zeros, which must stay zeros of the normalised tensor
+          const int iy = in_py + p.dy[f_tap], ix = in_px + p.dx[f_tap], iz = z0 + p.dz[f_tap];
+          const bool inb = iy >= 0 && iy < p.in_H && ix >= 0 && ix < p.in_W && iz >= 0 && iz < p.in_D;
+          const float4 sc = *reinterpret_cast<const float4*>(in_sc + f_cc * BK + 4 * j);
+          const float4 sh = *reinterpret_cast<const float4*>(in_sh + f_cc * BK + 4 * j);
+          a[0] = fmaf(a[0], sc.x, sh.x); a[1] = fmaf(a[1], sc.y, sh.y); a[2] = fmaf(a[2], sc.z, sh.z); a[3] = fmaf(a[3], sc.w, sh.w);
+          if (p.in_relu) { a[0] = fmaxf(a[0], 0.f); a[1] = fmaxf(a[1], 0.f); a[2] = fmaxf(a[2], 0.f); a[3] = fmaxf(a[3], 0.f); }
+          if (!inb) { a[0] = 0.f; a[1] = 0.f; a[2] = 0.f; a[3] = 0.f; }
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // hi = RN_tf32(a); lo = a - hi is exact in fp32 and |lo| <= 2^-12 |a|, so the tensor core's own
@@ -629,6 +674,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       // large images once the activation ring had its own, early, release).
       if (lane == 0) { mbar_arrive(bar_empty + 8 * s); mbar_arrive(bar_afull + 8 * b); }
       if (tr) p.dbg[blockIdx.x * 64 + 16 + (ks - 8) * 8 + 3] = clock64();
+      f_cc += GROUPS;
+      while (f_cc >= p.cin_chunks) { f_cc -= p.cin_chunks; ++f_tap; }
       s += GROUPS; if (s >= p.stages_a) { s -= p.stages_a; sph ^= 1u; }
       b += GROUPS; if (b >= p.nl) { b -= p.nl; bph ^= 1u; }
     }
@@ -1098,7 +1145,8 @@ int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, in
   // Ring depths (see the kernel): the weight ring gets everything the activation ring leaves. Budget per CTA:
   // the 227 KB opt-in maximum, or half of the SM's 228 KB minus the 1 KB per-CTA reservation for two CTAs.
   const size_t b_slot = 2 * (size_t)p.Cout_pad * BK * 4;
-  const size_t budget = (two_per_sm ? 115712 : 232448) - 512;          // 512 bytes of barriers
+  const size_t tbl = p.in_stats ? (size_t)2 * Cin_pad * 4 : 0;         // fused input BatchNorm: scale / shift tables
+  const size_t budget = (two_per_sm ? 115712 : 232448) - 512 - tbl;    // 512 bytes of barriers
   int stages_a = 4, stages = (int)((budget - 4 * (size_t)A_TILE_BYTES) / b_slot);
   if (stages < 5) { stages_a = 3; stages = (int)((budget - 3 * (size_t)A_TILE_BYTES) / b_slot); }
   if (stages > 8) stages = 8;
@@ -1109,7 +1157,8 @@ int launch_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, in
   size_t ring = (size_t)stages_a * A_TILE_BYTES + (size_t)stages * b_slot;
   const size_t ep_bytes = (size_t)((p.Cout_pad + 31) / 32) * 16384;    // output staging slabs alias the rings
   if (ring < ep_bytes) ring = ep_bytes;
-  const size_t smem = ring + 512;
+  const size_t smem = ring + 512 + tbl;
+  p.in_H = Hin; p.in_W = Win; p.in_D = Din;
   // TMA tensor store of the output tile: stride-1 outputs whose channel window starts on a 16-byte boundary
   CUtensorMap ty = ta;
   p.tma_store = 0;
@@ -1189,7 +1238,7 @@ int nrgbd_conv_nhwc_tc(const float* x_hi, const float* x_lo, int N, int Din, int
   NRGBD_REQUIRE(kd * kh * kw <= MAX_TAPS_TC && stride >= 1 && stride <= 8, "unsupported filter");
   NRGBD_REQUIRE(Hout == (Hin + 2 * pad - dilation * (kh - 1) - 1) / stride + 1 &&
                     Wout == (Win + 2 * pad - dilation * (kw - 1) - 1) / stride + 1, "output extent mismatch");
-  TcParams p;
+  TcParams p{};
   p.y = y; p.bias = bias; p.stats = stats;
   p.N = N; p.Dz = Din; p.Hy = Hout; p.Wx = Wout;
   p.in_stride = stride; p.Cout = Cout; p.Cout_pad = Cout_pad;
@@ -1221,7 +1270,7 @@ int nrgbd_conv_transpose2d_k4s2_nhwc_tc(const float* x_hi, const float* x_lo, in
   const int dys[2][2] = {{0, -1}, {1, 0}};
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
-      TcParams p;
+      TcParams p{};
       p.y = y; p.bias = bias; p.stats = nullptr;
       p.N = N; p.Dz = 1; p.Hy = Hin; p.Wx = Win;
       p.in_stride = 1; p.Cout = Cout; p.Cout_pad = Cout_pad;
@@ -1247,21 +1296,30 @@ int nrgbd_conv_tc2_supported(int Cin_pad, int Cout_pad) {
   return (Cin_pad % 32 == 0 && Cin_pad >= 32 && Cout_pad % 16 == 0 && Cout_pad >= 16 && Cout_pad <= 128) ? 1 : 0;
 }
 
-int nrgbd_conv_nhwc_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
-                        const float* w_lo, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw, int stride, int pad,
-                        int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, cudaStream_t st) {
+static int conv_nhwc_tc2_impl(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
+                              const float* w_lo, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw, int stride, int pad,
+                              int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats,
+                              const nrgbd_bn_input* in_bn, cudaStream_t st) {
   NRGBD_REQUIRE(x && w_hi && w_lo && y, "null pointer");
   NRGBD_REQUIRE(nrgbd_conv_tc2_supported(Cin_pad, Cout_pad) && Cin_pad <= Cs_in && Cs_in % 4 == 0 && Cout <= Cout_pad,
                 "channel counts not supported by the tensor-core path");
   NRGBD_REQUIRE(kd * kh * kw <= MAX_TAPS_TC && stride >= 1 && stride <= 8, "unsupported filter");
   NRGBD_REQUIRE(Hout == (Hin + 2 * pad - dilation * (kh - 1) - 1) / stride + 1 &&
                     Wout == (Win + 2 * pad - dilation * (kw - 1) - 1) / stride + 1, "output extent mismatch");
-  TcParams p;
+  TcParams p{};
   p.y = y; p.bias = bias; p.stats = stats;
   p.N = N; p.Dz = Din; p.Hy = Hout; p.Wx = Wout;
   p.in_stride = stride; p.Cout = Cout; p.Cout_pad = Cout_pad;
   p.Dout = Din; p.Hout = Hout; p.Wout = Wout; p.Cs_out = Cs_out; p.c_off = c_off;
   p.out_stride = 1; p.out_off_y = 0; p.out_off_x = 0; p.leaky = leaky;
+  p.in_stats = nullptr;
+  if (in_bn) {
+    NRGBD_REQUIRE(in_bn->stats && in_bn->gamma && in_bn->beta && in_bn->C >= 1 && in_bn->C <= Cin_pad && in_bn->count >= 1 &&
+                      in_bn->stats != stats, "bad input BatchNorm descriptor");
+    p.in_stats = in_bn->stats; p.in_count = in_bn->count; p.in_gamma = in_bn->gamma; p.in_beta = in_bn->beta;
+    p.in_run_mean = in_bn->running_mean && in_bn->running_var ? in_bn->running_mean : nullptr; p.in_run_var = in_bn->running_var;
+    p.in_eps = in_bn->eps; p.in_momentum = in_bn->momentum; p.in_relu = in_bn->relu; p.in_C = in_bn->C;
+  }
   int t = 0;
   for (int a = 0; a < kd; ++a)
     for (int b = 0; b < kh; ++b)
@@ -1277,6 +1335,24 @@ int nrgbd_conv_nhwc_tc2(const float* x, int N, int Din, int Hin, int Win, int Ci
   return NRGBD_OK;
 }
 
+int nrgbd_conv_nhwc_tc2(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
+                        const float* w_lo, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw, int stride, int pad,
+                        int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, cudaStream_t st) {
+  return conv_nhwc_tc2_impl(x, N, Din, Hin, Win, Cin_pad, Cs_in, w_hi, w_lo, bias, Cout, Cout_pad, kd, kh, kw, stride, pad, dilation, y,
+                            Hout, Wout, Cs_out, c_off, leaky, stats, nullptr, st);
+}
+
+// Same convolution of [relu](BatchNorm_train(x)) where x is the RAW output of the producing conv and in_bn carries its
+// per-channel sums: the normalisation is applied while the operands are converted (no separate pass over x).
+int nrgbd_conv_nhwc_tc2_bn_in(const float* x, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
+                              const float* w_lo, const float* bias, int Cout, int Cout_pad, int kd, int kh, int kw, int stride, int pad,
+                              int dilation, float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats,
+                              const nrgbd_bn_input* in_bn, cudaStream_t st) {
+  NRGBD_REQUIRE(in_bn, "null input BatchNorm descriptor");
+  return conv_nhwc_tc2_impl(x, N, Din, Hin, Win, Cin_pad, Cs_in, w_hi, w_lo, bias, Cout, Cout_pad, kd, kh, kw, stride, pad, dilation, y,
+                            Hout, Wout, Cs_out, c_off, leaky, stats, in_bn, st);
+}
+
 int nrgbd_conv_transpose2d_k4s2_nhwc_tc2(const float* x, int N, int Hin, int Win, int Cin_pad, int Cs_in, const float* w_hi,
                                          const float* w_lo, const float* bias, int Cout, int Cout_pad, float* y, int Cs_out,
                                          int c_off, int leaky, cudaStream_t st) {
@@ -1287,7 +1363,7 @@ int nrgbd_conv_transpose2d_k4s2_nhwc_tc2(const float* x, int N, int Hin, int Win
   const int dys[2][2] = {{0, -1}, {1, 0}};
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
-      TcParams p;
+      TcParams p{};
       p.y = y; p.bias = bias; p.stats = nullptr;
       p.N = N; p.Dz = 1; p.Hy = Hin; p.Wx = Win;
       p.in_stride = 1; p.Cout = Cout; p.Cout_pad = Cout_pad;

@@ -10,6 +10,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -81,7 +82,9 @@ struct nrgbd_kvnet {
   float* d_planes = nullptr;
   std::vector<float> d_host;
   Pool pool;
-  double* stats = nullptr;          // [2][512]
+  double* stats = nullptr;          // [2][512] per-channel sums of the conv in flight
+  double* stats_b = nullptr;        // second set: a conv that consumes one BatchNorm (fused) while producing the next
+  int fuse_bn = 1;                  // 1: fold BasicBlock's first BN+ReLU into the second conv where planes >= 64 (tensor path); 2: everywhere
   float* scale = nullptr;           // [512]
   float* shift = nullptr;           // [512]
   float* ws_sweep = nullptr;        // V*12
@@ -222,14 +225,16 @@ void split_act(Eng* e, const Act& x, Act& hi, Act& lo) {
 
 // conv (2-D when x.D == 1 and kd == 1) into a fresh activation or into `dst` at channel c_off
 Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k, int stride, int pad, int dil,
-         const char* bias_name, bool leaky, bool want_stats, Act* dst = nullptr, int c_off = 0, int out_Cs = -1) {
+         const char* bias_name, bool leaky, bool want_stats, Act* dst = nullptr, int c_off = 0, int out_Cs = -1,
+         double* stats_buf = nullptr, const nrgbd_bn_input* in_bn = nullptr) {
+  if (!stats_buf) stats_buf = e->stats;
   int Ho = (x.H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
   int Wo = (x.W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
   Act y;
   if (dst) y = *dst; else y = acquire(e, x.N, x.D, Ho, Wo, Cout, out_Cs);
   float* b = bias_name ? param(e, bias_name) : nullptr;
   if (e->rc) return y;
-  if (want_stats) cudaMemsetAsync(e->stats, 0, sizeof(double) * 2 * Cout, e->st);
+  if (want_stats) cudaMemsetAsync(stats_buf, 0, sizeof(double) * 2 * Cout, e->st);
   const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
   char tag[56];
   snprintf(tag, sizeof(tag), "conv%dd k%d s%d d%d %d->%d %dx%dx%dx%d", kd > 1 ? 3 : 2, k, stride, dil, x.C, Cout, x.N, x.D, Ho, Wo);
@@ -237,9 +242,15 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, kd * k * k, false);
     if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {       // in-kernel split, no extra pass
       ProfScope ps(e, 0, flops, tag);
-      ENG_CALL(e, nrgbd_conv_nhwc_tc2(x.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
-                                      stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
-                                      (nrgbd_stream_t)e->st));
+      if (in_bn) {
+        ENG_CALL(e, nrgbd_conv_nhwc_tc2_bn_in(x.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
+                                              stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? stats_buf : nullptr,
+                                              in_bn, (nrgbd_stream_t)e->st));
+      } else {
+        ENG_CALL(e, nrgbd_conv_nhwc_tc2(x.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
+                                        stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? stats_buf : nullptr,
+                                        (nrgbd_stream_t)e->st));
+      }
       return y;
     }
     Act xh, xl;
@@ -247,7 +258,7 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
     if (!e->rc) {
       ProfScope ps(e, 0, flops, tag);
       ENG_CALL(e, nrgbd_conv_nhwc_tc(xh.p, xl.p, x.N, x.D, x.H, x.W, pt->Cin_pad, x.Cs, pt->hi, pt->lo, b, Cout, pt->Cout_pad, kd, k, k,
-                                     stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
+                                     stride, pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? stats_buf : nullptr,
                                      (nrgbd_stream_t)e->st));
     }
     release(e, xh); release(e, xl);
@@ -257,7 +268,7 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   if (e->rc) return y;
   ProfScope ps(e, 0, flops, tag);
   ENG_CALL(e, nrgbd_conv_nhwc(x.p, x.N, x.D, x.H, x.W, pk->Cin_pad, x.Cs, pk->w, b, Cout, pk->Cout_pad, kd, k, k, stride,
-                              pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? e->stats : nullptr,
+                              pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? stats_buf : nullptr,
                               (nrgbd_stream_t)e->st));
   return y;
 }
@@ -278,9 +289,23 @@ Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k
   return y;
 }
 
+// Whether conv `Cin -> Cout` at this activation takes the in-kernel-split tensor path (the one that can fold an input BN)
+bool takes_tc2(Eng* e, const Act& x, int Cout) {
+  return use_tc(e, x, Cout) && nrgbd_conv_tc2_supported(pad32(x.C), pad16(Cout));
+}
+
 // psm_submodule.BasicBlock :31-49
 Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, int dil, bool down) {
-  Act t = convbn(e, x, pre + ".conv1.0", planes, 1, 3, stride, 1, dil, true, nullptr);
+  const int p1 = dil > 1 ? dil : 1;                  // psm_submodule.convbn :13
+  // Fused form (tensor path): conv1 leaves its RAW output and per-channel sums; BN1 + ReLU are applied by conv2 while it
+  // converts its operands (nrgbd_conv_nhwc_tc2_bn_in) - one read + one write of the 64/128-channel tensor less per block.
+  Act probe = x; probe.C = planes; probe.Cs = pad32(planes);
+  // Only where the consumer is not converter-bound: at 32 channels (N = 32 MMAs, two CTAs per SM) the operand converter is
+  // the critical warp and the extra fmaf/max per element costs more than the saved pass (measured: no net gain).
+  const bool fused = e->fuse_bn && (planes >= 64 || e->fuse_bn >= 2) && takes_tc2(e, x, planes) && takes_tc2(e, probe, planes);
+  Act t;
+  if (fused) t = conv(e, x, pre + ".conv1.0.0.weight", planes, 1, 3, stride, p1, dil, nullptr, false, true, nullptr, 0, -1, e->stats_b);
+  else t = convbn(e, x, pre + ".conv1.0", planes, 1, 3, stride, 1, dil, true, nullptr);
   Act sc; const Act* res = &x;
   if (down) {
     // downsample = Sequential(Conv2d 1x1 stride, BatchNorm2d) :125-131 -> names downsample.0 / downsample.1
@@ -294,7 +319,25 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
     }
     res = &sc;
   }
-  Act o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res);
+  Act o;
+  if (fused) {
+    nrgbd_bn_input bn;
+    bn.stats = e->stats_b; bn.count = (double)t.pos();
+    bn.gamma = param(e, pre + ".conv1.0.1.weight"); bn.beta = param(e, pre + ".conv1.0.1.bias");
+    bn.running_mean = e->bn_update_running ? param_opt(e, pre + ".conv1.0.1.running_mean") : nullptr;
+    bn.running_var = e->bn_update_running ? param_opt(e, pre + ".conv1.0.1.running_var") : nullptr;
+    bn.eps = 1e-5f; bn.momentum = 0.1f; bn.relu = 1; bn.C = planes;
+    o = conv(e, t, pre + ".conv2.0.weight", planes, 1, 3, 1, p1, dil, nullptr, false, true, nullptr, 0, -1, e->stats, &bn);
+    float* g = param(e, pre + ".conv2.1.weight"); float* b = param(e, pre + ".conv2.1.bias");
+    float* rm = e->bn_update_running ? param_opt(e, pre + ".conv2.1.running_mean") : nullptr;
+    float* rv = e->bn_update_running ? param_opt(e, pre + ".conv2.1.running_var") : nullptr;
+    if (!e->rc) {
+      ENG_CALL(e, nrgbd_bn_apply_stats(o.p, e->stats, (double)o.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
+                                       0.1f, res->p, 0, o.pos(), o.Cs, o.C, o.p, (nrgbd_stream_t)e->st));
+    }
+  } else {
+    o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res);
+  }
   release(e, t);
   if (down) release(e, sc);
   return o;
@@ -313,9 +356,39 @@ Act make_layer(Eng* e, Act x, bool own_x, const std::string& pre, int planes, in
 // psm_submodule.feature_extraction.forward :141-167 -> (layer1 output @1/2, features @1/4)
 void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
   const std::string P = "feature_extractor.feature_extraction";
-  Act a = convbn(e, x0, P + ".firstconv.0", 32, 1, 3, 2, 1, 1, true, nullptr);
-  Act b = convbn(e, a, P + ".firstconv.2", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, a);
-  Act c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, b);
+  // firstconv = convbn+ReLU x3 (psm_submodule.py:90-92). Tensor path: the first two BatchNorm+ReLU are folded into the
+  // conv that consumes them (the raw 5x240x320x32 tensors are read once by the next conv instead of read+written+read).
+  Act c;
+  Act probe32 = x0; probe32.C = 32; probe32.Cs = pad32(32); probe32.H = (x0.H + 2 - 3) / 2 + 1; probe32.W = (x0.W + 2 - 3) / 2 + 1;
+  if (e->fuse_bn >= 2 && takes_tc2(e, probe32, 32)) {            // development setting only: slower than the separate pass (see basic_block)
+    auto bn_of = [&](const std::string& pre, double* stats, const Act& t) {
+      nrgbd_bn_input bn;
+      bn.stats = stats; bn.count = (double)t.pos();
+      bn.gamma = param(e, pre + ".1.weight"); bn.beta = param(e, pre + ".1.bias");
+      bn.running_mean = e->bn_update_running ? param_opt(e, pre + ".1.running_mean") : nullptr;
+      bn.running_var = e->bn_update_running ? param_opt(e, pre + ".1.running_var") : nullptr;
+      bn.eps = 1e-5f; bn.momentum = 0.1f; bn.relu = 1; bn.C = 32;
+      return bn;
+    };
+    Act a = conv(e, x0, P + ".firstconv.0.0.weight", 32, 1, 3, 2, 1, 1, nullptr, false, true, nullptr, 0, pad32(32), e->stats_b);
+    nrgbd_bn_input bn_a = bn_of(P + ".firstconv.0", e->stats_b, a);
+    Act b = conv(e, a, P + ".firstconv.2.0.weight", 32, 1, 3, 1, 1, 1, nullptr, false, true, nullptr, 0, -1, e->stats, &bn_a);
+    release(e, a);
+    nrgbd_bn_input bn_b = bn_of(P + ".firstconv.2", e->stats, b);
+    c = conv(e, b, P + ".firstconv.4.0.weight", 32, 1, 3, 1, 1, 1, nullptr, false, true, nullptr, 0, -1, e->stats_b, &bn_b);
+    release(e, b);
+    float* g = param(e, P + ".firstconv.4.1.weight"); float* bb = param(e, P + ".firstconv.4.1.bias");
+    float* rm = e->bn_update_running ? param_opt(e, P + ".firstconv.4.1.running_mean") : nullptr;
+    float* rv = e->bn_update_running ? param_opt(e, P + ".firstconv.4.1.running_var") : nullptr;
+    if (!e->rc) {
+      ENG_CALL(e, nrgbd_bn_apply_stats(c.p, e->stats_b, (double)c.pos(), g, bb, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
+                                       0.1f, nullptr, 1, c.pos(), c.Cs, c.C, c.p, (nrgbd_stream_t)e->st));
+    }
+  } else {
+    Act a = convbn(e, x0, P + ".firstconv.0", 32, 1, 3, 2, 1, 1, true, nullptr);
+    Act b = convbn(e, a, P + ".firstconv.2", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, a);
+    c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, b);
+  }
   Act l1 = make_layer(e, c, true, P + ".layer1", 32, 3, 1, 1, false);
   Act raw = make_layer(e, l1, false, P + ".layer2", 64, 16, 2, 1, true);
   Act l3 = make_layer(e, raw, false, P + ".layer3", 128, 3, 1, 1, true);
@@ -482,7 +555,9 @@ int nrgbd_kvnet_create(int H, int W, int D, int V, int feature_dim, int kv_featu
   e->H = H; e->W = W; e->D = D; e->V = V; e->F = feature_dim; e->KF = kv_feature_dim;
   e->h = H / 4; e->w = W / 4; e->sigma = sigma; e->metric = metric;
   const size_t hw = (size_t)e->h * e->w;
+  if (const char* fb = getenv("NRGBD_FUSE_BN")) e->fuse_bn = atoi(fb);      // development A/B switch
   bool ok = cudaMalloc((void**)&e->stats, sizeof(double) * 2 * 512) == cudaSuccess &&
+            cudaMalloc((void**)&e->stats_b, sizeof(double) * 2 * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->scale, sizeof(float) * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->shift, sizeof(float) * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->ws_sweep, sizeof(float) * 12 * V) == cudaSuccess &&
@@ -502,7 +577,7 @@ int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
   for (auto& kv : e->packed) cudaFree(kv.second.w);
   for (auto& kv : e->packed_tc) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
   for (int i = 0; i < 2; ++i) { cudaFree(e->cam[i].K); cudaFree(e->cam[i].rays); }
-  cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
+  cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->stats_b); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
   cudaFree(e->bv_cur_hwd); cudaFree(e->dpv_hwd); cudaFree(e->prior_hwd); cudaFree(e->depth); cudaFree(e->conf);
   cudaFree(e->x0_buf); cudaFree(e->rt_buf); cudaFree(e->ref_cur_hwd); cudaFree(e->ref_kv_hwd);
   drop_graphs(e);
@@ -578,6 +653,7 @@ int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value) {
   std::string k(key);
   if (k == "bn_update_running") { drop_graphs(e); e->bn_update_running = value; return NRGBD_OK; }
   if (k == "profile") { e->profile = value; return NRGBD_OK; }
+  if (k == "fuse_bn") { if (e->fuse_bn != value) drop_graphs(e); e->fuse_bn = value; return NRGBD_OK; }
   if (k == "use_graph") { drop_graphs(e); e->use_graph = value; return NRGBD_OK; }
   if (k == "conv_math") {            // 0: exact fp32 (CUDA cores); 1: tcgen05 3xTF32 (tensor cores)
     if (value != 0 && value != 1) { nrgbd_set_error("conv_math must be 0 (fp32) or 1 (tf32x3)"); return NRGBD_ERR_BAD_ARG; }

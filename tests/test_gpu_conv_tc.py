@@ -119,3 +119,35 @@ def test_tc2_large_images_repeatable(shape):
     for _ in range(3):
         y = convops.conv_tc(x, w, None, 1, 1, 1, impl='v2')
         assert float((y - ref).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize('cfg', [dict(N=2, C=64, H=24, W=40, Co=64, s=1, p=1, d=1), dict(N=1, C=32, H=37, W=53, Co=32, s=1, p=1, d=1),
+                                 dict(N=5, C=128, H=30, W=40, Co=128, s=1, p=2, d=2), dict(N=2, C=32, H=48, W=64, Co=64, s=2, p=1, d=1),
+                                 dict(N=1, C=67, H=40, W=56, Co=64, s=1, p=1, d=1)])
+def test_conv_with_fused_input_batchnorm(cfg):
+    """BasicBlock's conv1 -> BN(batch statistics) -> ReLU -> conv2 with the BN+ReLU folded into conv2's operand converter
+    (psm_submodule.py:31-49): bit-identical to the stand-alone BN pass followed by the same convolution - the operands
+    the tensor core sees are the same floats - including the zero padding and the running-statistics update."""
+    from neuralrgbd_b200 import convops
+    g = torch.Generator(device='cuda').manual_seed(21)
+    x = torch.randn((cfg['N'], 32, cfg['H'], cfg['W']), device='cuda', generator=g)
+    w1 = torch.randn((cfg['C'], 32, 3, 3), device='cuda', generator=g) / math.sqrt(32 * 9)
+    w2 = torch.randn((cfg['Co'], cfg['C'], 3, 3), device='cuda', generator=g) / math.sqrt(cfg['C'] * 9)
+    gamma = torch.rand(cfg['C'], device='cuda', generator=g) + 0.5
+    beta = torch.randn(cfg['C'], device='cuda', generator=g) * 0.3
+    y1, st1 = convops.conv_tc(x, w1, None, 1, 1, 1, want_stats=True, impl='v2')         # raw conv1 output + its sums
+    ref_in = convops.batch_norm(y1, st1, gamma, beta, relu=True)
+    want, st_want = convops.conv_tc(ref_in, w2, None, cfg['s'], cfg['p'], cfg['d'], want_stats=True, impl='v2')
+    rm = torch.zeros(cfg['C'], device='cuda'); rv = torch.ones(cfg['C'], device='cuda')
+    got, st_got = convops.conv_tc_bn_in(y1, st1, gamma, beta, w2, None, cfg['s'], cfg['p'], cfg['d'], relu=True, want_stats=True,
+                                        running=(rm, rv))
+    assert torch.equal(got, want)
+    assert float((st_got - st_want).abs().max()) <= 1e-9 * float(st_want.abs().max())
+    # running statistics as torch's training-mode BatchNorm updates them (momentum 0.1, unbiased variance)
+    mean = y1.mean(dim=(0, 2, 3)); var = y1.var(dim=(0, 2, 3), unbiased=True)
+    assert float((rm - 0.1 * mean).abs().max()) <= 1e-6 and float((rv - (0.9 + 0.1 * var)).abs().max()) <= 1e-5
+    # and against torch itself (fp32 reference of the whole fused op)
+    import torch.nn.functional as F
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):        # cuDNN defaults to TF32 convolutions
+        t = F.conv2d(F.relu(F.batch_norm(y1, None, None, gamma, beta, True, 0.1, 1e-5)), w2, None, cfg['s'], cfg['p'], cfg['d'])
+    assert float((got - t).abs().max()) <= 2e-5 * float(t.abs().max())
