@@ -1,7 +1,18 @@
-"""Mirror of the reference's inference step `test_utils.test_KVNet.test`
-(/root/reference/code/test_utils/test_KVNet.py:19-67): one KVNET forward for the reference
-frame of a window, then propagation of the resulting DPV into the next camera. Same signature
-and return values; works with the engine-backed KVNET (optionally wrapped in nn.DataParallel)."""
+"""Inference step of the streaming loop, behind the reference's name and signature:
+`test_utils.test_KVNet.test` (/root/reference/code/test_utils/test_KVNet.py:19-67).
+
+What one call does (reference line numbers):
+  1. window tensors from the frame dicts: reference image [B,3,H,W], sources [B,V,3,H,W]   (:30-33)
+  2. one KVNET forward under no_grad with the predicted prior                               (:35-40)
+  3. first frame of a trajectory (prior None): the measured DPV stands in for the filtered  (:42-44)
+  4. prior for the NEXT frame: the filtered low-resolution DPV resampled into the next camera
+     (pose = inverse of the given next pose, or of the window's (t_win_r)-th source pose), faces padded
+     with log(1/D), result clamped to [-1000, 0]                                            (:46-62)
+  5. returns (refined full-resolution DPV if R_net else filtered DPV, stacked priors)       (:64-67)
+Here step 4 is one fused device kernel per batch entry (resample + pad + clamp), the frames are moved with
+`.cuda()` only if they are not on a device yet, and the model may be the engine-backed KVNET or that module
+wrapped in nn.DataParallel - both expose the same keyword interface as the reference's.
+"""
 import math
 
 import numpy as np
@@ -10,41 +21,43 @@ import torch
 from ..warping import homography as warp_homo
 
 
+def _on_device(t):
+    return t if t.is_cuda else t.cuda()
+
+
+def _stack_window(Ref_Dats, Src_Dats):
+    """Frame dicts -> (ref [B,3,H,W], src [B,V,3,H,W])."""
+    ref = torch.cat([_on_device(d['img']) for d in Ref_Dats], dim=0)
+    per_traj = [torch.cat([_on_device(f['img']) for f in traj], dim=0) for traj in Src_Dats]
+    return ref, torch.stack(per_traj, dim=0)
+
+
+def _next_prior(dpv_lowres, pose_to_next, cam_intrinsic, d_candi):
+    """Step 4 for one batch entry: [D,h,w] log-DPV -> [1,D,h,w] prior in the next camera."""
+    uniform_log = math.log(1.0 / float(len(d_candi)))
+    moved = warp_homo.resample_vol_cuda(src_vol=dpv_lowres.unsqueeze(0), rel_extM=pose_to_next.inverse(),
+                                        cam_intrinsic=cam_intrinsic, d_candi=d_candi, padding_value=uniform_log,
+                                        clamp=(-1000., 0.))
+    return moved.unsqueeze(0)
+
+
 def test(model_KV, d_candi, Cam_Intrinsics, t_win_r, Ref_Dats, Src_Dats, Src_CamPoses, BV_predict,
          cam_pose_next=None, R_net=False, Cam_Intrinsics_imgsize=None, ref_indx=None):
-    '''
-    Test the trained KV-Net
-    '''
-    nGPU = 1   # should set to 1 for testing (test_KVNet.py:27)
-    BatchIdx_range = torch.FloatTensor(np.arange(nGPU))
-    ref_frame = torch.cat(tuple([ref_dat['img'].cuda() for ref_dat in Ref_Dats]), dim=0)
-    src_frames_list = [torch.cat(tuple([src_dat_frame['img'].cuda() for src_dat_frame in src_dats_traj]),
-                                 dim=0).unsqueeze(0) for src_dats_traj in Src_Dats]
-    src_frames = torch.cat(tuple(src_frames_list), dim=0)
-
+    """One depth frame of the stream. Arguments and return values as the reference (see module docstring);
+    `Cam_Intrinsics_imgsize` and `ref_indx` are accepted and unused, as there."""
+    ref_frame, src_frames = _stack_window(Ref_Dats, Src_Dats)
+    batch_ids = torch.FloatTensor(np.arange(1))          # nGPU is fixed to 1 for testing (:27-28)
     with torch.no_grad():
-        dmap_cur_refined, dmap_refined, d_dpv, kv_dpv = model_KV(
-            ref_frame=ref_frame, src_frames=src_frames, src_cam_poses=Src_CamPoses, BatchIdx=BatchIdx_range,
+        refined_cur, refined_filtered, dpv_measured, dpv_filtered = model_KV(
+            ref_frame=ref_frame, src_frames=src_frames, src_cam_poses=Src_CamPoses, BatchIdx=batch_ids,
             cam_intrinsics=Cam_Intrinsics, BV_predict=BV_predict)
+    first_of_trajectory = BV_predict is None
+    if first_of_trajectory:
+        dpv_filtered, refined_filtered = dpv_measured, refined_cur
 
-    if BV_predict is None:   # if the first frame in the sequence
-        kv_dpv = d_dpv
-        dmap_refined = dmap_cur_refined
-
-    # BV_predict estimation (3D re-sampling): resample + clamp fused in one kernel
-    BVs_predict = []
-    for ibatch in range(d_dpv.shape[0]):
-        if cam_pose_next is None:
-            rel_Rt = Src_CamPoses[ibatch, t_win_r, :, :].inverse()
-        else:
-            rel_Rt = cam_pose_next.inverse()
-        BV_predict = warp_homo.resample_vol_cuda(src_vol=kv_dpv[ibatch, ...].unsqueeze(0), rel_extM=rel_Rt,
-                                                 cam_intrinsic=Cam_Intrinsics[ibatch], d_candi=d_candi,
-                                                 padding_value=math.log(1. / float(len(d_candi))),
-                                                 clamp=(-1000., 0.)).unsqueeze(0)
-        BVs_predict.append(BV_predict)
-    BVs_predict = torch.cat(BVs_predict, dim=0)
-    if R_net:
-        return dmap_refined, BVs_predict
-    else:
-        return kv_dpv, BVs_predict
+    priors = []
+    for b in range(dpv_measured.shape[0]):
+        pose = cam_pose_next if cam_pose_next is not None else Src_CamPoses[b, t_win_r, :, :]
+        priors.append(_next_prior(dpv_filtered[b], pose, Cam_Intrinsics[b], d_candi))
+    BVs_predict = torch.cat(priors, dim=0)
+    return (refined_filtered if R_net else dpv_filtered), BVs_predict
