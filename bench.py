@@ -107,20 +107,24 @@ def make_windows(n_windows, seed=7):
 # reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores
 # ----------------------------------------------------------------------------------------------
 def pick_cpu_threads():
-    """Thread count for the CPU arm: the fastest of {all cores, 64, 32, 16, 8} on a short calibration conv
-    (on many-core hosts torch's intra-op pool oversubscribes: 128 threads ran this path 6x slower than 8)."""
+    """Thread count for the CPU arm: the fastest of {all cores, 64, 32, 16, 8} on a short calibration over the three conv
+    shapes that dominate the frame (on many-core hosts torch's intra-op pool oversubscribes: 128 threads ran this path 6x
+    slower than 8, and which count wins differs from host to host)."""
     import torch
     import torch.nn.functional as F
     n_all = os.cpu_count() or 1
     cands = sorted({c for c in (n_all, 64, 32, 16, 8) if c <= n_all}, reverse=True)
-    x = torch.randn(5, 32, 120, 160); w = torch.randn(32, 32, 3, 3)
+    work = [(torch.randn(5, 64, 120, 160), torch.randn(64, 64, 3, 3)), (torch.randn(5, 128, 120, 160), torch.randn(128, 128, 3, 3)),
+            (torch.randn(5, 32, 240, 320), torch.randn(32, 32, 3, 3))]
     best, best_t = cands[0], None
     for c in cands:
         torch.set_num_threads(c)
-        F.conv2d(x, w, padding=1)
-        t0 = time.perf_counter()
-        for _ in range(3):
+        for x, w in work:
             F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            for x, w in work:
+                F.conv2d(x, w, padding=1)
         t = time.perf_counter() - t0
         if best_t is None or t < best_t:
             best, best_t = c, t

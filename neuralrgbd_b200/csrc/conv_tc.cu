@@ -7,17 +7,22 @@
 // a_lo = RN_tf32(a - a_hi) and the product is accumulated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo in
 // the fp32 TMEM accumulator (dropped term <= 2^-22 |a b|).
 //
-// Structure (one 128-pixel x Cout output tile per CTA):
-//   warp 0    TMA producer: per K-step (one filter tap x 32 input channels) four bulk-tensor loads -
-//             an 8x16-pixel x 32-channel box of the hi and lo activation tensors (5-D tensor map over
-//             [N][D][H][W][C]; padding = TMA out-of-bounds zero fill, conv stride = element stride,
-//             dilation / transposed-conv parity = box origin) and the hi / lo weight slices, all in the
-//             128-byte-swizzled K-major layout tcgen05 consumes; mbarrier expect-tx pipeline.
-//   warp 1    MMA issuer: 4 K-slices x 3 tcgen05.mma.kind::tf32 (M=128, N=Cout_pad, K=8) per step into
-//             a TMEM accumulator; tcgen05.commit releases the smem stage / signals the epilogue.
-//   warps 2-5 epilogue: tcgen05.ld 32x32b (one output pixel per thread), bias / LeakyReLU, vector
-//             stores to the channels-last output, BatchNorm sum / sum-of-squares via a smem
-//             transpose and one double atomicAdd per channel per CTA.
+// Two kernels share the helpers below (one 128-pixel x Cout output tile per CTA in both):
+//
+// conv_tc2_kernel<GROUPS>  - the production kernel (DESIGN.md 4.2 has the measurements behind every choice)
+//   warp 0      TMA producer: per K-step (one filter tap x 32 input channels) an 8x16-pixel x 32-channel box of the RAW
+//               activation (5-D tensor map over [N][D][H][W][C]; padding = TMA out-of-bounds zero fill, conv stride =
+//               element stride, dilation / transposed-conv parity = box origin) into the activation ring, and the
+//               hi / lo weight slices into the weight ring; 128-byte-swizzled K-major tiles, mbarrier expect-tx.
+//   warps 2-5   (+ 7-10 when the CTA owns the SM) operand converters: one pixel row per thread, optional BatchNorm+ReLU
+//               of the input, hi / lo split in registers, tcgen05.st into a TMEM operand buffer; then the epilogue:
+//               tcgen05.ld, fp32 sum of the accumulators, bias / LeakyReLU, swizzled staging tile in shared memory,
+//               cp.async.bulk.tensor stores per 32-channel slab, BatchNorm column sums from the same tile.
+//   warp 1      MMA issuer (software-pipelined): a_hi x [b_hi | b_lo] as one MMA of width 2 Cout, a_lo x b_hi as a
+//               second, A from TMEM, B from shared memory; tcgen05.commit frees the weight slot / operand buffer.
+// conv_tc_kernel  - v1, kept as the fallback for Cout_pad > 128 and as a measured reference point: operands pre-split
+//   in global memory (nrgbd_split_tf32), four TMA loads per K-step, both operands from shared memory, two issue
+//   streams, direct vector stores.
 #include <cstdlib>
 #include <cuda.h>
 
