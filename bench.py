@@ -119,8 +119,11 @@ def pick_cpu_threads():
     best, best_t = cands[0], None
     for c in cands:
         torch.set_num_threads(c)
+        t0 = time.perf_counter()
         for x, w in work:
             F.conv2d(x, w, padding=1)
+        if best_t is not None and time.perf_counter() - t0 > 4 * best_t:
+            continue                                   # hopeless (oversubscribed): do not spend more time on it
         t0 = time.perf_counter()
         for _ in range(2):
             for x, w in work:
