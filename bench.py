@@ -113,7 +113,7 @@ def pick_cpu_threads():
     import torch
     import torch.nn.functional as F
     n_all = os.cpu_count() or 1
-    cands = sorted({c for c in (n_all, 64, 32, 16, 8) if c <= n_all}, reverse=True)
+    cands = sorted({c for c in (n_all, 64, 32, 16, 8) if c <= n_all})      # ascending: a hopeless large count is cut short
     work = [(torch.randn(5, 64, 120, 160), torch.randn(64, 64, 3, 3)), (torch.randn(5, 128, 120, 160), torch.randn(128, 128, 3, 3)),
             (torch.randn(5, 32, 240, 320), torch.randn(32, 32, 3, 3))]
     best, best_t = cands[0], None
