@@ -89,6 +89,15 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.rows), 'reasons': sorted(reasons)}
 
 
+def conv_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch (mean over the 70 conv launches of one frame) from the
+    committed ncu capture profiles/r1b_conv_dram_traffic.json (bytes); None if the file is missing."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'profiles', 'r1b_conv_dram_traffic.json')))['traffic_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 def make_windows(n_windows, seed=7):
     """n_windows seeded 5-frame windows: frames [V+1,3,H,W] (sources then reference, basic.py:245) and
     relative poses [V,4,4]."""
@@ -408,7 +417,8 @@ def run_engine(args):
             'gpu_launches': launches,
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': conv_tflops, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': conv_tflops / peak_tf,
-                         'traffic': None, 'kernel': ('conv_tc2_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)' if args.conv_math == 'tf32x3' else 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)') + ', %d launches/step, avg %.1f us (CUDA events around every conv launch in %d eager frames run right after the timed graph replays)' % (conv_n // P_PROF, 1e3 * conv_ms / max(conv_n, 1), P_PROF),
+                         'traffic': conv_traffic_per_launch() if args.conv_math == 'tf32x3' else None, 'kernel': ('conv_tc2_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)' if args.conv_math == 'tf32x3' else 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)') + ', %d launches/step, avg %.1f us (CUDA events around every conv launch in %d eager frames run right after the timed graph replays)' % (conv_n // P_PROF, 1e3 * conv_ms / max(conv_n, 1), P_PROF),
+                         'traffic_note': 'bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the 70 conv launches of one frame, ncu capture profiles/r1b_conv_dram_traffic.json (2.46 GB read + 0.28 GB written per frame)',
                          'peak_source': peaks['source'] + ', sustained bf16'},
         }
         # cpu baseline: bounded sample of the same workload through the oracle port (rank 0, N = 1 only)
