@@ -447,3 +447,74 @@ def est_swp_volume_v4_backward(grad_cost, feat_img_ref, feat_img_src, d_candi, R
                 for c in range(C):
                     np.add.at(gsrc[v, c], idx.reshape(-1), contrib[c])
     return gref.reshape(1, C, h, w).astype(f32), gsrc.reshape(1, V, C, h, w).astype(f32)
+
+
+# --------------------------------------------------------------------------
+# f-3 (oracle first; the device kernels are the next round's work): depth-map back-warp used by the
+# local bundle adjustment, warping/homography.py:479-574 (back_warp_th_Rt, back_warp_th_Rt_msrc), and
+# its pose gradients (ICP/opt_pose_numerical.py differentiates the warped image w.r.t. R, t through the
+# sampling grid: F.grid_sample backward w.r.t. the grid, the perspective division, the two matmuls).
+# --------------------------------------------------------------------------
+def _warp_points(dmap, R, t, cam_intrinsic):
+    """Pixel grid of the source view for every reference pixel: X = d * ray, P = K (R X + t), u = P_x/P_z, v = P_y/P_z,
+    normalised (u - cx)/cx, (v - cy)/cy (:546-567). Returns gx, gy [H*W] and the intermediates the backward needs."""
+    K = np.asarray(cam_intrinsic['intrinsic_M_cuda'], f32)
+    rays = np.asarray(cam_intrinsic['unit_ray_array_2D'], f32)
+    d = np.asarray(dmap, f32).reshape(1, -1)
+    X = (d * rays).astype(f32)                                        # [3, n]
+    Xc = (np.asarray(R, f32) @ X + np.asarray(t, f32).reshape(3, 1)).astype(f32)
+    P = (K @ Xc).astype(f32)
+    u = (P[0] / P[2]).astype(f32); v = (P[1] / P[2]).astype(f32)
+    cx, cy = K[0, 2], K[1, 2]
+    return ((u - cx) / cx).astype(f32), ((v - cy) / cy).astype(f32), X, Xc, P
+
+
+def back_warp_th_Rt(img_src, dmap, R, t, cam_intrinsic):
+    """warping/homography.py:531-574: img_src [1,C,H,W] sampled at the projection of the reference depth map."""
+    img = np.asarray(img_src, f32)[0]
+    C, H, W = img.shape
+    gx, gy, _, _, _ = _warp_points(dmap, R, t, cam_intrinsic)
+    return grid_sample_2d_zeros(img, gx.reshape(H, W), gy.reshape(H, W))[None]
+
+
+def back_warp_th_Rt_msrc(imgs_src, dmap, Rs, ts, cam_intrinsic):
+    """warping/homography.py:479-529: the same warp for N source frames [N,C,H,W] with their own poses."""
+    return np.concatenate([back_warp_th_Rt(imgs_src[i:i + 1], dmap, Rs[i], ts[i], cam_intrinsic) for i in range(len(imgs_src))], 0)
+
+
+def back_warp_th_Rt_backward(grad_out, img_src, dmap, R, t, cam_intrinsic):
+    """Gradients of back_warp_th_Rt w.r.t. R [3,3], t [3] and img_src [1,C,H,W] for grad_out [1,C,H,W] (float64 sums).
+    grid_sample backward w.r.t. the grid (ATen grid_sampler_2d_backward, bilinear / zeros / align_corners=False):
+    d out/d ix = sum over the 4 corners of value * d weight/d ix, times size/2 from the un-normalisation."""
+    img = np.asarray(img_src, f32)[0]
+    g = np.asarray(grad_out, np.float64)[0]
+    C, H, W = img.shape
+    K = np.asarray(cam_intrinsic['intrinsic_M_cuda'], np.float64)
+    gx, gy, X, Xc, P = _warp_points(dmap, R, t, cam_intrinsic)
+    ix = _unnormalize(gx, W).astype(np.float64); iy = _unnormalize(gy, H).astype(np.float64)
+    x0 = np.floor(ix); y0 = np.floor(iy)
+    flat = img.reshape(C, -1).astype(np.float64)
+    g_flat = g.reshape(C, -1)
+    g_img = np.zeros((C, H * W), np.float64)
+    g_ix = np.zeros(H * W); g_iy = np.zeros(H * W)
+    for dx, dy in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        xx = x0 + dx; yy = y0 + dy
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H) & np.isfinite(ix) & np.isfinite(iy)
+        idx = np.where(ok, yy * W + xx, 0).astype(np.int64)
+        wx = (1 - np.abs(ix - xx)); wy = (1 - np.abs(iy - yy))              # bilinear weights of this corner
+        val = np.where(ok[None], flat[:, idx], 0.0)
+        gv = (g_flat * val).sum(0)                                          # sum_c grad * value
+        g_ix += np.where(ok, gv * wy * (1.0 if dx else -1.0), 0.0)
+        g_iy += np.where(ok, gv * wx * (1.0 if dy else -1.0), 0.0)
+        contrib = g_flat * np.where(ok, wx * wy, 0.0)[None]
+        for c in range(C):
+            np.add.at(g_img[c], idx, contrib[c])
+    cx, cy = K[0, 2], K[1, 2]
+    g_u = g_ix * (W / 2.0) / cx                                             # ix = ((u-cx)/cx + 1) * W/2 - 1/2
+    g_v = g_iy * (H / 2.0) / cy
+    Pd = P.astype(np.float64)
+    g_P = np.stack([g_u / Pd[2], g_v / Pd[2], -(g_u * Pd[0] + g_v * Pd[1]) / (Pd[2] * Pd[2])])   # [3, n]
+    g_Xc = K.T @ g_P
+    g_R = g_Xc @ X.astype(np.float64).T
+    g_t = g_Xc.sum(1)
+    return g_R.astype(f32), g_t.astype(f32), g_img.reshape(1, C, H, W).astype(f32)

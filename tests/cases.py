@@ -187,3 +187,19 @@ def preprocess_case(name):
 
 
 PREPROCESS_CASES = ['pre_down_97x131_to_64x48', 'pre_up_37x53_to_80x64', 'pre_same_48x64', 'pre_odd_100x100_to_77x33']
+
+
+# ---- f-3 (oracle pinned ahead of the kernels): depth-map back-warp of the local bundle adjustment ------------------
+def lba_case(name):
+    """-> imgs [N,C,h,w], dmap [h,w], Rs [N,3,3], ts [N,3], w, h."""
+    cfg = {'lba_v1_c5_37x53': dict(N=1, C=5, h=37, w=53, seed=51, step_t=0.05),
+           'lba_v3_c3_48x64': dict(N=3, C=3, h=48, w=64, seed=52, step_t=0.08)}[name]
+    rng = np.random.RandomState(cfg['seed'])
+    imgs = rng.standard_normal((cfg['N'], cfg['C'], cfg['h'], cfg['w'])).astype(np.float32)
+    dmap = (0.8 + 2.5 * rng.rand(cfg['h'], cfg['w'])).astype(np.float32)
+    poses = _poses(rng, cfg['N'], step_t=cfg['step_t'])
+    return dict(imgs=imgs, dmap=dmap, Rs=np.ascontiguousarray(poses[:, :3, :3]), ts=np.ascontiguousarray(poses[:, :3, 3]),
+                w=cfg['w'], h=cfg['h'])
+
+
+LBA_CASES = ['lba_v1_c5_37x53', 'lba_v3_c3_48x64']
