@@ -72,3 +72,26 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
     want = [ctypes.sizeof(B)] + [getattr(B, f).offset for f in ('stats', 'count', 'gamma', 'beta', 'running_mean', 'running_var',
                                                                  'eps', 'momentum', 'relu', 'C')]
     assert got == want
+
+
+def test_c_program_links_and_uses_the_library(tmp_path):
+    """examples/write_depth_pgm.c - a plain C host (no Python, torch or CUDA headers) - compiles against include/nrgbd.h,
+    links libnrgbd.so and produces the reference's 16-bit PGM format."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from oracle import export_oracle as E
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        import pytest
+        pytest.skip('no C compiler')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / 'write_depth_pgm')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), os.path.join(ROOT, 'examples', 'write_depth_pgm.c'),
+                        '-L', libdir, '-lnrgbd', '-Wl,-rpath,' + libdir, '-o', exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = str(tmp_path / 'd.pgm')
+    r = subprocess.run([exe, out, '64', '48'], capture_output=True, text=True)
+    assert r.returncode == 0 and 'ABI 1' in r.stdout, r.stdout + r.stderr
+    yy, xx = np.mgrid[0:48, 0:64]
+    assert open(out, 'rb').read() == E.pgm16_bytes((500 + 7 * xx + 3 * yy).astype(np.uint16))
