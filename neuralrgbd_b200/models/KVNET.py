@@ -128,23 +128,33 @@ class KVNET(nn.Module):
             self._engines[key] = ent
         return ent
 
+    def _resolve(self, name):
+        """Tensor registered under the dotted state_dict name, found by walking attributes: works on the module
+        itself and on an nn.DataParallel replica (replicate() re-attaches the broadcast copies as plain tensor
+        attributes, so a replica's named_parameters() is empty)."""
+        node = self
+        for part in name.split('.'):
+            node = getattr(node, part)
+        return node
+
     def _param_list(self):
         """(name, tensor) for every float parameter / buffer the engine needs, cached per module object
         (a DataParallel replica is a new object each forward and rebuilds it)."""
         cache = self.__dict__.get('_plist')
         if cache is None or cache[0] != id(self):
-            sd = dict(self.named_parameters())
-            sd.update({k: v for k, v in self.named_buffers()})
-            cache = (id(self), [(name, sd[name]) for name, shape, kind in self._specs if kind != 'bn_nb'])
+            cache = (id(self), [(name, self._resolve(name)) for name, shape, kind in self._specs if kind != 'bn_nb'])
             self.__dict__['_plist'] = cache
         return cache[1]
 
     def _sync_params(self, ent, device):
         L = _lib.lib()
         seen = ent['params']
+        # a DataParallel replica holds fresh broadcast copies every forward: the caching allocator may hand back an
+        # address the engine has seen (same data_ptr, version 0) with new contents, so replicas always re-register
+        replica = bool(getattr(self, '_is_replica', False))
         for name, t in self._param_list():
             tag = (t.data_ptr(), t._version)
-            if seen.get(name) != tag:
+            if replica or seen.get(name) != tag:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise _lib.NrgbdError('parameter %s must be a contiguous float32 tensor on %s (call .cuda())' % (name, device))
                 check(L.nrgbd_kvnet_set_param(ent['h'], name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), 1))
@@ -153,29 +163,40 @@ class KVNET(nn.Module):
     def _flush_batches_tracked(self, *args, **kwargs):
         """BatchNorm's num_batches_tracked side effect (training mode) is applied lazily: one counter per
         forward on the host, materialised into the 15 buffers when the state_dict is read."""
-        n = self.__dict__.get('_nb_pending', 0)
-        if n:
+        n_all = self.__dict__.get('_nb_pending', 0)          # every forward: the feature-CNN BatchNorms
+        n_kv = self.__dict__.get('_nb_pending_kv', 0)        # forwards that ran K-Net (valid prior): kv_net BatchNorm3d
+        if n_all or n_kv:
             for name, _, kind in self._specs:
                 if kind == 'bn_nb':
-                    self.get_buffer(name).add_(n)
+                    n = n_kv if name.startswith('kv_net.') else n_all
+                    if n:
+                        self.get_buffer(name).add_(n)
             self.__dict__['_nb_pending'] = 0
+            self.__dict__['_nb_pending_kv'] = 0
 
     def _set_camera(self, ent, slot, cam=None, IntM=None, rays=None):
         L = _lib.lib()
         if cam is not None:
-            tag = id(cam)
-            if ent['cams'][slot] == tag:
-                return
+            # keyed by CONTENT of the small members (K, principal point, fovs) and identity + version of the ray
+            # table: an in-place edit of the dict, or another trajectory's dict at a recycled id(), is seen
+            rays_t = torch.as_tensor(cam['unit_ray_array_2D'])
             K = np.ascontiguousarray(torch.as_tensor(cam['intrinsic_M_cuda']).detach().cpu().numpy().astype(np.float32))
-            R = np.ascontiguousarray(torch.as_tensor(cam['unit_ray_array_2D']).detach().cpu().numpy().astype(np.float32))
             cx, cy = float(cam['intrinsic_M'][0, 2]), float(cam['intrinsic_M'][1, 2])
             hf, vf = float(cam.get('hfov', 0.)), float(cam.get('vfov', 0.))
-            ent['keep'][slot] = cam
-        else:
-            tag = (IntM.data_ptr(), rays.data_ptr())
+            tag = (id(cam), K.tobytes(), cx, cy, hf, vf, rays_t.data_ptr(), rays_t._version, tuple(rays_t.shape))
             if ent['cams'][slot] == tag:
                 return
-            K = np.ascontiguousarray(IntM.detach().reshape(3, 3).cpu().numpy().astype(np.float32))
+            R = np.ascontiguousarray(rays_t.detach().cpu().numpy().astype(np.float32))
+            ent['keep'][slot] = cam
+        else:
+            # scattered tensors are re-allocated every forward and the allocator recycles addresses: key by content
+            # (K and a checksum of the ray table, one small device->host read)
+            sig = torch.cat([IntM.detach().reshape(-1)[:9].float(), rays.detach().float().sum().reshape(1),
+                             rays.detach().float().abs().max().reshape(1)]).cpu().numpy()
+            tag = (sig.tobytes(), tuple(rays.shape))
+            if ent['cams'][slot] == tag:
+                return
+            K = np.ascontiguousarray(sig[:9].reshape(3, 3).astype(np.float32))
             R = np.ascontiguousarray(rays.detach().reshape(3, -1).cpu().numpy().astype(np.float32))
             cx, cy = float(K[0, 2]), float(K[1, 2])
             hf = math.degrees(math.atan(cx / K[0, 0]) * 2); vf = math.degrees(math.atan(cy / K[1, 1]) * 2)
@@ -243,7 +264,13 @@ class KVNET(nn.Module):
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             check(L.nrgbd_kvnet_forward(ent['h'], ptr(frames), ptr(poses), ptr(prior), ptr(dmap_cur), ptr(dmap_kv),
                                         ptr(bv_cur), ptr(dpv), ptr(depth), ptr(conf), st))
-            self.__dict__['_nb_pending'] = self.__dict__.get('_nb_pending', 0) + 1   # BatchNorm side effect, applied lazily
+            # BatchNorm's num_batches_tracked side effect, applied lazily; a replica shares the counters' owner
+            owner = self.__dict__.get('_owner_ref', None)
+            owner = owner() if owner is not None else self
+            if owner is not None:
+                owner.__dict__['_nb_pending'] = owner.__dict__.get('_nb_pending', 0) + 1
+                if prior is not None:
+                    owner.__dict__['_nb_pending_kv'] = owner.__dict__.get('_nb_pending_kv', 0) + 1
         if prior is None:
             out = (dmap_cur, dmap_cur, bv_cur, bv_cur)     # KVNET.py:138-143
         else:
@@ -272,10 +299,23 @@ class KVNET(nn.Module):
             check(L.nrgbd_kvnet_propagate(ent['h'], ptr(src), ptr(E), ptr(out), st))
         return out
 
+    def _replicate_for_data_parallel(self):
+        """nn.DataParallel replica: shares the engine table with its owner (engines are keyed by device, one per
+        GPU) but never owns the native handles - only the module that created the table destroys them."""
+        import weakref
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__['_owner_ref'] = self.__dict__.get('_owner_ref') or weakref.ref(self)
+        replica.__dict__.pop('_plist', None)
+        return replica
+
     def __del__(self):
+        if self.__dict__.get('_is_replica', False) or self.__dict__.get('_owner_ref') is not None:
+            return                      # handles belong to the owner module
         try:
             L = _lib.lib()
-            for ent in self._engines.values():
+            engines = self.__dict__.get('_engines') or {}
+            for ent in list(engines.values()):
                 L.nrgbd_kvnet_destroy(ent['h'])
+            engines.clear()
         except Exception:
             pass

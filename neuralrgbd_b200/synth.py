@@ -66,7 +66,7 @@ def video(seed, n_frames, H, W, parallax=0.0):
     """n_frames images [3,H,W]; consecutive frames are shifted copies of one smooth
     texture plus per-frame noise so that costs have structure."""
     rng = np.random.RandomState(seed)
-    pad = 64
+    pad = 64 if n_frames <= 20 else 8 + 6 * (n_frames // 2 + 1)      # long streams need a wider texture margin
     base = smooth_image(rng, 3, H + 2 * pad, W + 2 * pad)
     frames = []
     for i in range(n_frames):

@@ -131,6 +131,51 @@ def kvnet_case(name):
 KVNET_CASES = ['kvnet_256_d16', 'kvnet_256x320_d8']
 
 
+# ---- the BASELINE.json configurations at (or standing in for) their full sizes ----------------------------------
+# Fixtures: tests/golden/make_golden_configs.py (live reference, FREE-RUNNING: every step is fed the reference's own
+# propagated prior; the engine under test feeds its own, so the comparison includes the drift of the recursion).
+KITTI = dict(fx=721.5377, fy=721.5377, cx=624.0, cy=188.0)     # KITTI-like pinhole centred on the 1248x376 frame
+BIG_CFG = {
+    # configs[1] (first window = step 0) and configs[2] (30-frame stream, steps 1..29 steady state with K-Net)
+    'c23_640x480_d64_v4_stream30': dict(seed=61, H=480, W=640, D=64, n_frames=34, wseed=7, t_win_r=2),
+    # configs[3]: the reference CNN rejects 1242x375, 1248x376 is the nearest legal frame; KITTI planes
+    'c4_1248x376_d128_v4': dict(seed=63, H=376, W=1248, D=128, n_frames=6, wseed=8, t_win_r=2, d_min=1.0, d_max=60.0,
+                                intr=KITTI),
+    # configs[4] stand-in at the smallest legal frame: V=8 (K-Net 28 input channels), D=256 (R-Net 320 channels)
+    'c5s_256x256_d256_v8': dict(seed=64, H=256, W=256, D=256, n_frames=10, wseed=9, t_win_r=4),
+}
+BIG_CASES = list(BIG_CFG)
+# steps whose four outputs are stored at the normal sub-sampling; later steps store the filtered DPV + refined DPV thinner
+BIG_FULL_STEPS = 4
+
+
+def big_case(name, n_frames=None):
+    cfg = BIG_CFG[name]
+    nf = cfg['n_frames']
+    frames, rng = synth.video(cfg['seed'], nf, cfg['H'], cfg['W'])
+    exts = synth.camera_track(rng, nf)
+    r = cfg['t_win_r']
+    sd = arch.synth_state_dict(cfg['wseed'], 64, cfg['D'], r, 64)
+    d = synth.d_candidates(cfg['D'], cfg.get('d_min', 0.1), cfg.get('d_max', 5.0))
+    intr = cfg.get('intr', dict(fx=FX, fy=FY, cx=CX, cy=CY))
+    return dict(frames=frames, exts=exts, sd=sd, d=d, H=cfg['H'], W=cfg['W'], D=cfg['D'], sigma=10.0, t_win_r=r,
+                intr=intr, n_steps=nf - 2 * r)
+
+
+def big_cam(make_cam, c):
+    i = c['intr']
+    return make_cam(i['fx'], i['fy'], i['cx'], i['cy'], [c['W'] // 4, c['H'] // 4])
+
+
+def subsample_to(a, limit):
+    """subsample() with an explicit size limit (strides up to 64)."""
+    a = np.asarray(a)
+    step = 1
+    while a[..., ::step, ::step].size > limit and step < 64:
+        step += 1
+    return np.ascontiguousarray(a[..., ::step, ::step])
+
+
 def window(case, ref_idx):
     """ref frame [1,3,H,W], src [1,V,3,H,W], poses [1,V,4,4] for the 5-frame window
     centred on ref_idx (mutils/misc.py:509-517)."""
@@ -203,3 +248,12 @@ def lba_case(name):
 
 
 LBA_CASES = ['lba_v1_c5_37x53', 'lba_v3_c3_48x64']
+
+
+# ---- a14: calibrations pushed through the reference's intrinsics recipe (tests/golden/make_golden_camera.py) -------
+CAMERA_CASES = {
+    '7scenes_to_160x120': dict(width=640, height=480, fx=585.0, fy=585.0, cx=320.0, cy=240.0, out_size=[160, 120]),
+    'scannet_to_96x64': dict(width=1296, height=968, fx=1170.187988, fy=1170.187988, cx=647.75, cy=483.75, out_size=[96, 64]),
+    'kitti_to_312x94': dict(width=1248, height=376, fx=721.5377, fy=721.5377, cx=624.0, cy=188.0, out_size=[312, 94]),
+    'offcentre_ragged_53x37': dict(width=640, height=480, fx=600.0, fy=590.0, cx=300.0, cy=250.0, out_size=[53, 37]),
+}
