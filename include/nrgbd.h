@@ -14,6 +14,8 @@
  *    boundary. nrgbd_last_error() returns a thread-local message for the last failure.
  *  - the caller owns every buffer; the library keeps no hidden global state besides the launch
  *    counter. All entry points are re-entrant and launch on the stream they are given.
+ *  - development probes and A/B knobs are NOT part of this header: see include/nrgbd_dev.h (not bound by the
+ *    product's Python layer; no environment variable changes what a product entry point runs).
  */
 #ifndef NRGBD_H_
 #define NRGBD_H_
@@ -185,11 +187,6 @@ int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const
  * (nrgbd_split_tf32, nrgbd_pack_conv_weight_tc -> [taps][Cout_pad][Cin_pad]). Semantics otherwise
  * identical to nrgbd_conv_nhwc / nrgbd_conv_transpose2d_k4s2_nhwc. */
 int nrgbd_conv_tc_supported(int Cin_pad, int Cout_pad);   /* Cin_pad % 32 == 0, Cout_pad % 16 == 0, <= 256 */
-void nrgbd_conv_tc_set_nacc(int n);  /* development knob: cap on the rotating main accumulators (0 = auto) */
-void nrgbd_conv_tc_set_dev(int stages, int flags); /* development knobs: ring depth cap; A/B flags listed in csrc/conv_tc.cu */
-void nrgbd_conv_tc_set_debug_buffer(long long* device_buf); /* development: [grid][64] clock64 stamps (tools/tc_timeline.py) */
-int nrgbd_mma_probe(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, int n_ctas, long long* out,
-                    nrgbd_stream_t stream);   /* development: raw tcgen05.mma rate probe */
 int nrgbd_split_tf32(const float* x, long long n, float* hi, float* lo, nrgbd_stream_t stream);
 int nrgbd_pack_conv_weight_tc(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad,
                               int Cout_pad, float* hi, float* lo, nrgbd_stream_t stream);
@@ -230,6 +227,24 @@ int nrgbd_conv_transpose2d_k4s2_nhwc_tc2(const float* x, int N, int Hin, int Win
                                          const float* w_hi, const float* w_lo, const float* bias, int Cout,
                                          int Cout_pad, float* y, int Cs_out, int c_off, int leaky,
                                          nrgbd_stream_t stream);
+/* Second-generation tensor-core path (csrc/conv_f16.cu): tcgen05 kind::f16 on SPLIT-FP16 operand pairs, fp32 accumulate.
+ * Every fp32 value a is carried as two halves, a = hi + lo * 2^-11 (hi = RN_f16(a), lo = RN_f16((a - hi) * 2^11)), and a
+ * product is accumulated as hi*hi + 2^-11 (hi*lo + lo*hi): the 22-bit product of the 3xTF32 path at twice the MMA rate
+ * and half the operand bytes. Activations are consumed in pair form (two half tensors with the fp32 tensor's
+ * channels-last layout and channel stride) from nrgbd_split_f16_pair / the fused BatchNorm pass; weights are packed once
+ * by nrgbd_pack_conv_weight_h2 -> [taps][2 (hi | lo)][Cout_pad][Cin_pad] halves. Stride-1 filters stage ONE halo tile per
+ * 32-channel chunk for all in-plane taps (the tap-per-box kernels re-read the tile kh*kw times from L2).
+ * Same convolution semantics, outputs (fp32) and BatchNorm statistics as nrgbd_conv_nhwc. */
+int nrgbd_conv_h2_plan(int Cin, int Cout, int* Cin_pad, int* Cout_pad, int* BN);   /* channel padding: Cin to 32; Cout into equal chunks of BN <= 128 */
+int nrgbd_split_f16_pair(const float* x, long long n, void* hi, void* lo, nrgbd_stream_t stream);
+int nrgbd_pack_conv_weight_h2(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad, int Cout_pad, void* out,
+                              nrgbd_stream_t stream);
+int nrgbd_conv_nhwc_h2(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const void* w,
+                       const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride, int pad, int dilation,
+                       float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, nrgbd_stream_t stream);
+int nrgbd_conv_transpose2d_k4s2_nhwc_h2(const void* x_hi, const void* x_lo, int N, int Hin, int Win, int Cin_pad, int Cs_in,
+                                        const void* w, const float* bias, int Cout, int Cout_pad, int BN, float* y, int Cs_out,
+                                        int c_off, int leaky, nrgbd_stream_t stream);
 /* layout / pooling helpers (P = positions per image) */
 int nrgbd_nchw_to_nhwc(const float* x, int N, int C, long long P, float* y, int Cs, int c_off,
                        nrgbd_stream_t stream);
@@ -260,7 +275,7 @@ int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, l
 int nrgbd_kvnet_set_camera(nrgbd_kvnet* e, int slot, const float* K_host, const float* rays_host, float cx,
                            float cy, double hfov_deg, double vfov_deg);
 int nrgbd_kvnet_set_planes(nrgbd_kvnet* e, const float* d_host, int D);   /* float32(d_candi) */
-int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value);   /* "bn_update_running", "profile", "conv_math" (0 fp32 FFMA, 1 tcgen05 3xTF32), "use_graph" (CUDA-graph replay, default 1) */
+int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value);   /* "bn_update_running", "profile", "conv_math" (0 fp32 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 split-fp16 pairs), "use_graph" (CUDA-graph replay, default 1) */
 /* with option "profile"=1 the engine brackets its conv (category 0, work = flops) and plane-sweep
  * (category 1, work = algorithmic bytes) launches with CUDA events; this returns and clears the sums. */
 int nrgbd_kvnet_profile_read(nrgbd_kvnet* e, int category, double* ms, double* work, long long* launches);

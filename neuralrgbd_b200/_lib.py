@@ -38,10 +38,6 @@ SIGNATURES = {
     'nrgbd_conv_transpose2d_k4s2_nhwc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int,
                                                  c_vp, c_int, c_int, c_int, c_vp]),
     'nrgbd_conv_tc_supported': (c_int, [c_int, c_int]),
-    'nrgbd_conv_tc_set_nacc': (None, [c_int]),
-    'nrgbd_conv_tc_set_dev': (None, [c_int, c_int]),
-    'nrgbd_conv_tc_set_debug_buffer': (None, [c_vp]),
-    'nrgbd_mma_probe': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'nrgbd_split_tf32': (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp]),
     'nrgbd_pack_conv_weight_tc': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'nrgbd_conv_nhwc_tc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int,
@@ -58,6 +54,14 @@ SIGNATURES = {
                                           c_vp, c_vp]),
     'nrgbd_conv_transpose2d_k4s2_nhwc_tc2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int,
                                                      c_int, c_vp, c_int, c_int, c_int, c_vp]),
+    'nrgbd_conv_h2_plan': (c_int, [c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    'nrgbd_split_f16_pair': (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp]),
+    'nrgbd_pack_conv_weight_h2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'nrgbd_conv_nhwc_h2': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp,
+                                   c_vp]),
+    'nrgbd_conv_transpose2d_k4s2_nhwc_h2': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int,
+                                                    c_int, c_vp, c_int, c_int, c_int, c_vp]),
     'nrgbd_bn_finalize': (c_int, [c_vp, c_int, ctypes.c_double, c_vp, c_vp, c_float, c_vp, c_vp, c_vp, c_vp,
                                   c_float, c_vp]),
     'nrgbd_bn_apply_stats': (c_int, [c_vp, c_vp, ctypes.c_double, c_vp, c_vp, c_float, c_vp, c_vp, c_float, c_vp, c_int, c_ll,
@@ -89,6 +93,18 @@ SIGNATURES = {
     'nrgbd_kvnet_propagate': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
+# include/nrgbd_dev.h: development probes / A-B knobs. Bound only by dev_lib() (tools/, kernel-variant tests), never by the
+# product modules.
+DEV_SIGNATURES = {
+    'nrgbd_conv_tc_set_nacc': (None, [c_int]),
+    'nrgbd_conv_tc_set_dev': (None, [c_int, c_int]),
+    'nrgbd_conv_tc_set_debug_buffer': (None, [c_vp]),
+    'nrgbd_mma_probe': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'nrgbd_dev_conv_h2_set_flags': (None, [c_int]),
+    'nrgbd_dev_conv_h2_set_debug_buffer': (None, [c_vp]),
+}
+
+
 class BnInput(ctypes.Structure):
     """include/nrgbd.h: nrgbd_bn_input."""
     _fields_ = [('stats', c_vp), ('count', ctypes.c_double), ('gamma', c_vp), ('beta', c_vp), ('running_mean', c_vp),
@@ -116,6 +132,18 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def dev_lib():
+    """The library with the development entry points of include/nrgbd_dev.h bound as well (tools and variant tests only)."""
+    L = lib()
+    if not getattr(L, '_nrgbd_dev_bound', False):
+        for name, (res, args) in DEV_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        L._nrgbd_dev_bound = True
+    return L
 
 
 def check(rc):

@@ -249,3 +249,76 @@ def conv_tc_bn_in(x_raw, in_stats, gamma, beta, w, bias=None, stride=1, pad=0, d
                                       ctypes.c_void_p(stats.data_ptr()) if want_stats else None, ctypes.byref(d), _st()))
     out = from_cl(y, Cout)
     return (out, stats) if want_stats else out
+
+
+# ---------------------------------------------------------------------------------------------
+# second-generation tensor-core path (csrc/conv_f16.cu): tcgen05 kind::f16 on split-fp16 operand pairs
+# ---------------------------------------------------------------------------------------------
+def h2_plan(Cin, Cout):
+    L = _lib.lib()
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert L.nrgbd_conv_h2_plan(Cin, Cout, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 1
+    return a.value, b.value, c.value          # Cin_pad, Cout_pad, BN
+
+
+def split_f16_pair(xc):
+    """fp32 tensor -> (hi, lo) float16 tensors of the same shape: x = hi + lo * 2^-11."""
+    L = _lib.lib()
+    hi = torch.empty(xc.shape, device=xc.device, dtype=torch.float16); lo = torch.empty_like(hi)
+    check(L.nrgbd_split_f16_pair(ptr(xc), xc.numel(), ptr(hi), ptr(lo), _st()))
+    return hi, lo
+
+
+def pack_weight_h2(w, transposed=False):
+    L = _lib.lib()
+    if transposed:
+        Cin, Cout = w.shape[0], w.shape[1]
+    else:
+        Cout, Cin = w.shape[0], w.shape[1]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    Cin_pad, Cout_pad, BN = h2_plan(Cin, Cout)
+    out = torch.empty((taps, 2, Cout_pad, Cin_pad), device=w.device, dtype=torch.float16)
+    check(L.nrgbd_pack_conv_weight_h2(ptr(w.float().contiguous()), 1 if transposed else 0, Cout, Cin, taps, Cin_pad, Cout_pad,
+                                      ptr(out), _st()))
+    return out, Cin_pad, Cout_pad, BN
+
+
+def conv_h2(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stats=False):
+    """f16-pair tensor-core counterpart of conv() (same arguments / returns)."""
+    L = _lib.lib()
+    is3d = x.dim() == 5
+    N = x.shape[0]
+    Din = x.shape[2] if is3d else 1
+    Hin, Win = x.shape[-2], x.shape[-1]
+    Cout, Cin = w.shape[0], w.shape[1]
+    wp, Cin_pad, Cout_pad, BN = pack_weight_h2(w)
+    xc = to_cl_padded(x, Cin_pad)
+    xh, xl = split_f16_pair(xc)
+    kd = w.shape[2] if is3d else 1
+    kh, kw = w.shape[-2], w.shape[-1]
+    Ho = (Hin + 2 * pad - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (Win + 2 * pad - dilation * (kw - 1) - 1) // stride + 1
+    Cs_out = pad4(Cout)
+    y = torch.zeros((N,) + ((Din,) if is3d else ()) + (Ho, Wo, Cs_out), device=x.device, dtype=torch.float32)
+    stats = torch.zeros((2, Cout), device=x.device, dtype=torch.float64) if want_stats else None
+    check(L.nrgbd_conv_nhwc_h2(ptr(xh), ptr(xl), N, Din, Hin, Win, Cin_pad, Cin_pad, ptr(wp), ptr(bias), Cout, Cout_pad, BN,
+                               kd, kh, kw, stride, pad, dilation, ptr(y), Ho, Wo, Cs_out, 0, 1 if leaky else 0,
+                               ctypes.c_void_p(stats.data_ptr()) if want_stats else None, _st()))
+    out = from_cl(y, Cout)
+    return (out, stats) if want_stats else out
+
+
+def conv_transpose2d_h2(x, w, bias=None, leaky=False):
+    L = _lib.lib()
+    N, Cin, Hin, Win = x.shape
+    Cout = w.shape[1]
+    wp, Cin_pad, Cout_pad, BN = pack_weight_h2(w, transposed=True)
+    xc = to_cl_padded(x, Cin_pad)
+    xh, xl = split_f16_pair(xc)
+    Cs_out = pad4(Cout)
+    y = torch.zeros((N, 2 * Hin, 2 * Win, Cs_out), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_conv_transpose2d_k4s2_nhwc_h2(ptr(xh), ptr(xl), N, Hin, Win, Cin_pad, Cin_pad, ptr(wp), ptr(bias), Cout,
+                                                Cout_pad, BN, ptr(y), Cs_out, 0, 1 if leaky else 0, _st()))
+    return from_cl(y, Cout)

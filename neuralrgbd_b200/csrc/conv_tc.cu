@@ -27,7 +27,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "../../include/nrgbd.h"
+#include "../../include/nrgbd_dev.h"
 
 namespace {
 
@@ -988,14 +988,12 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int kind, int
 int g_force_nacc = 0;
 int g_force_stages = 0;     // development knobs (nrgbd_conv_tc_set_dev)
 long long* g_dbg = nullptr;
-// development A/B switch without recompiling: NRGBD_TC_DEV=<flags> in the environment seeds g_dev_flags
-int env_dev_flags() { const char* v = getenv("NRGBD_TC_DEV"); return v ? atoi(v) : 0; }
-// Development knobs (nrgbd_conv_tc_set_dev / NRGBD_TC_DEV), all off in production:
+// Development knobs (nrgbd_conv_tc_set_dev, include/nrgbd_dev.h), all off unless a tool sets them:
 //   1    v1: plain 1xTF32 (hi*hi only)            2    never two CTAs per SM        4    v1: single issue stream
 //   8    v2: two issue streams                    16   skip the BN statistics       32   skip the output stores
 //   64   v2: one converter / epilogue group       128  v2: two TMEM operand buffers 2048 v2: direct stores instead of TMA stores
 //   4096 v2: three-MMA K-slices with rotating main accumulators instead of the concatenated two-MMA form
-int g_dev_flags = env_dev_flags();
+int g_dev_flags = 0;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -53,6 +53,8 @@ struct Pool {           // stream-ordered reuse of cudaMalloc'd blocks (single s
 struct ParamRef { float* p; long long n; bool owned; };
 struct Packed { float* w; int Cin, Cin_pad, Cout, Cout_pad, taps; };
 struct PackedTc { float* hi; float* lo; int Cin_pad, Cout_pad, taps; };
+struct PackedH2 { void* w; int Cin_pad, Cout_pad, BN, taps; };       // f16-pair tiles [taps][2][Cout_pad][Cin_pad] halves
+struct PairBuf { float* hi; float* lo; };                          // split-fp16 planes of an activation (pool blocks)
 
 struct Camera {
   bool set = false;
@@ -76,7 +78,9 @@ struct nrgbd_kvnet {
   std::unordered_map<std::string, ParamRef> params;
   std::unordered_map<std::string, Packed> packed;
   std::unordered_map<std::string, PackedTc> packed_tc;
-  int conv_math = 0;                // 0: exact fp32 FFMA implicit GEMM; 1: tcgen05 3xTF32 where supported
+  std::unordered_map<std::string, PackedH2> packed_h2;
+  std::unordered_map<const float*, PairBuf> pairs;   // activations that currently have a split-fp16 copy (conv_math 2)
+  int conv_math = 0;                // 0: exact fp32 FFMA implicit GEMM; 1: tcgen05 3xTF32; 2: tcgen05 split-fp16 pairs (conv_f16.cu)
   bool packed_dirty = true;
   Camera cam[2];
   float* d_planes = nullptr;
@@ -147,14 +151,38 @@ struct ProfScope {
 
 Act acquire(Eng* e, int N, int D, int H, int W, int C, int Cs = -1) {
   Act a; a.N = N; a.D = D; a.H = H; a.W = W; a.C = C;
-  a.Cs = Cs >= 0 ? Cs : ((e->conv_math == 1 && C >= 16) ? pad32(C) : pad4(C));   // tensor-core K-steps are 32 channels
+  a.Cs = Cs >= 0 ? Cs : ((e->conv_math >= 1 && C >= 16) ? pad32(C) : pad4(C));   // tensor-core K-steps are 32 channels
   if (e->rc) return a;
   a.p = e->pool.acquire((size_t)a.floats() * sizeof(float));
   if (!a.p) { nrgbd_set_error("engine: out of device memory (%lld floats)", a.floats()); e->rc = NRGBD_ERR_NOMEM; return a; }
   if (a.Cs != a.C) cudaMemsetAsync(a.p, 0, (size_t)a.floats() * sizeof(float), e->st);   // pad channels must be 0
   return a;
 }
-void release(Eng* e, Act& a) { if (a.p) e->pool.release(a.p); a.p = nullptr; }
+void release(Eng* e, Act& a) {
+  if (a.p) {
+    auto it = e->pairs.find(a.p);
+    if (it != e->pairs.end()) { e->pool.release(it->second.hi); e->pool.release(it->second.lo); e->pairs.erase(it); }
+    e->pool.release(a.p);
+  }
+  a.p = nullptr;
+}
+
+// Split-fp16 operand planes of an activation (x = hi + lo * 2^-11), created on first use by a convolution and kept
+// until the activation is released: several convolutions may consume the same tensor (BasicBlock input: conv1 +
+// downsample). Activations are never written again after their first conv consumer has run.
+const PairBuf* pair_of(Eng* e, const Act& x) {
+  auto it = e->pairs.find(x.p);
+  if (it != e->pairs.end()) return &it->second;
+  if (e->rc) return nullptr;
+  PairBuf pb;
+  const size_t bytes = (size_t)x.floats() * 2;
+  pb.hi = e->pool.acquire(bytes);
+  pb.lo = e->pool.acquire(bytes);
+  if (!pb.hi || !pb.lo) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return nullptr; }
+  ENG_CALL(e, nrgbd_split_f16_pair(x.p, x.floats(), pb.hi, pb.lo, (nrgbd_stream_t)e->st));
+  e->pairs[x.p] = pb;
+  return &e->pairs[x.p];
+}
 
 float* param(Eng* e, const std::string& name) {
   auto it = e->params.find(name);
@@ -209,6 +237,31 @@ const PackedTc* packw_tc(Eng* e, const std::string& name, int Cout, int Cin, int
   return &e->packed_tc[name];
 }
 
+const PackedH2* packw_h2(Eng* e, const std::string& name, int Cout, int Cin, int taps, bool transposed) {
+  auto it = e->packed_h2.find(name);
+  if (it != e->packed_h2.end()) return &it->second;
+  float* src = param(e, name);
+  if (!src) return nullptr;
+  auto pr = e->params[name];
+  if (pr.n != (long long)Cout * Cin * taps) {
+    if (e->rc == 0) { nrgbd_set_error("engine: parameter '%s' has %lld elements, expected %lld", name.c_str(), pr.n, (long long)Cout * Cin * taps); e->rc = NRGBD_ERR_BAD_ARG; }
+    return nullptr;
+  }
+  PackedH2 pk; pk.taps = taps;
+  nrgbd_conv_h2_plan(Cin, Cout, &pk.Cin_pad, &pk.Cout_pad, &pk.BN);
+  void* q = nullptr;
+  if (cudaMalloc(&q, (size_t)taps * 2 * pk.Cin_pad * pk.Cout_pad * 2) != cudaSuccess) { e->rc = NRGBD_ERR_NOMEM; nrgbd_set_error("engine: cudaMalloc failed for packed weight"); return nullptr; }
+  pk.w = q;
+  ENG_CALL(e, nrgbd_pack_conv_weight_h2(src, transposed ? 1 : 0, Cout, Cin, taps, pk.Cin_pad, pk.Cout_pad, pk.w, (nrgbd_stream_t)e->st));
+  e->packed_h2[name] = pk;
+  return &e->packed_h2[name];
+}
+
+// f16-pair tensor path: any conv with >= 16 input channels whose activation carries the 32-channel padding
+bool use_h2(Eng* e, const Act& x) {
+  return e->conv_math == 2 && x.C >= 16 && pad32(x.C) <= x.Cs && x.Cs % 8 == 0;
+}
+
 bool use_tc(Eng* e, const Act& x, int Cout) {
   return e->conv_math == 1 && nrgbd_conv_tc_supported(pad32(x.C), pad16(Cout)) && pad32(x.C) <= x.Cs;
 }
@@ -238,6 +291,15 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
   char tag[56];
   snprintf(tag, sizeof(tag), "conv%dd k%d s%d d%d %d->%d %dx%dx%dx%d", kd > 1 ? 3 : 2, k, stride, dil, x.C, Cout, x.N, x.D, Ho, Wo);
+  if (use_h2(e, x)) {
+    const PackedH2* ph = packw_h2(e, wname, Cout, x.C, kd * k * k, false);
+    const PairBuf* pb = pair_of(e, x);
+    if (e->rc) return y;
+    ProfScope ps(e, 0, flops, tag);
+    ENG_CALL(e, nrgbd_conv_nhwc_h2(pb->hi, pb->lo, x.N, x.D, x.H, x.W, ph->Cin_pad, x.Cs, ph->w, b, Cout, ph->Cout_pad, ph->BN, kd, k, k, stride,
+                                   pad, dil, y.p, Ho, Wo, y.Cs, c_off, leaky ? 1 : 0, want_stats ? stats_buf : nullptr, (nrgbd_stream_t)e->st));
+    return y;
+  }
   if (use_tc(e, x, Cout)) {
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, kd * k * k, false);
     if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {       // in-kernel split, no extra pass
@@ -444,6 +506,15 @@ void conv_transpose(Eng* e, const Act& x, const std::string& wname, const char* 
   const double flops = 2.0 * 4.0 * (double)x.H * x.W * Cout * x.C * 4;
   char tag[56];
   snprintf(tag, sizeof(tag), "convT k4 s2 %d->%d %dx%dx%d", x.C, Cout, x.N, 2 * x.H, 2 * x.W);
+  if (use_h2(e, x)) {
+    const PackedH2* ph = packw_h2(e, wname, Cout, x.C, 16, true);
+    const PairBuf* pb = pair_of(e, x);
+    if (e->rc) return;
+    ProfScope ps(e, 0, flops, tag);
+    ENG_CALL(e, nrgbd_conv_transpose2d_k4s2_nhwc_h2(pb->hi, pb->lo, x.N, x.H, x.W, ph->Cin_pad, x.Cs, ph->w, tb, Cout, ph->Cout_pad, ph->BN,
+                                                    dst.p, dst.Cs, 0, 1, st));
+    return;
+  }
   if (use_tc(e, x, Cout)) {
     const PackedTc* pt = packw_tc(e, wname, Cout, x.C, 16, true);
     if (!e->rc && nrgbd_conv_tc2_supported(pt->Cin_pad, pt->Cout_pad)) {
@@ -555,7 +626,6 @@ int nrgbd_kvnet_create(int H, int W, int D, int V, int feature_dim, int kv_featu
   e->H = H; e->W = W; e->D = D; e->V = V; e->F = feature_dim; e->KF = kv_feature_dim;
   e->h = H / 4; e->w = W / 4; e->sigma = sigma; e->metric = metric;
   const size_t hw = (size_t)e->h * e->w;
-  if (const char* fb = getenv("NRGBD_FUSE_BN")) e->fuse_bn = atoi(fb);      // development A/B switch
   bool ok = cudaMalloc((void**)&e->stats, sizeof(double) * 2 * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->stats_b, sizeof(double) * 2 * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->scale, sizeof(float) * 512) == cudaSuccess &&
@@ -576,6 +646,7 @@ int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
   for (auto& kv : e->params) if (kv.second.owned) cudaFree(kv.second.p);
   for (auto& kv : e->packed) cudaFree(kv.second.w);
   for (auto& kv : e->packed_tc) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+  for (auto& kv : e->packed_h2) cudaFree(kv.second.w);
   for (int i = 0; i < 2; ++i) { cudaFree(e->cam[i].K); cudaFree(e->cam[i].rays); }
   cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->stats_b); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
   cudaFree(e->bv_cur_hwd); cudaFree(e->dpv_hwd); cudaFree(e->prior_hwd); cudaFree(e->depth); cudaFree(e->conf);
@@ -607,6 +678,8 @@ int nrgbd_kvnet_set_param(nrgbd_kvnet* e, const char* name, const float* data, l
   if (pk != e->packed.end()) { cudaFree(pk->second.w); e->packed.erase(pk); }
   auto pt = e->packed_tc.find(key);
   if (pt != e->packed_tc.end()) { cudaFree(pt->second.hi); cudaFree(pt->second.lo); e->packed_tc.erase(pt); }
+  auto p2 = e->packed_h2.find(key);
+  if (p2 != e->packed_h2.end()) { cudaFree(p2->second.w); e->packed_h2.erase(p2); }
   ParamRef r; r.n = n; r.owned = !is_device;
   if (is_device) {
     r.p = const_cast<float*>(data);
@@ -655,8 +728,8 @@ int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value) {
   if (k == "profile") { e->profile = value; return NRGBD_OK; }
   if (k == "fuse_bn") { if (e->fuse_bn != value) drop_graphs(e); e->fuse_bn = value; return NRGBD_OK; }
   if (k == "use_graph") { drop_graphs(e); e->use_graph = value; return NRGBD_OK; }
-  if (k == "conv_math") {            // 0: exact fp32 (CUDA cores); 1: tcgen05 3xTF32 (tensor cores)
-    if (value != 0 && value != 1) { nrgbd_set_error("conv_math must be 0 (fp32) or 1 (tf32x3)"); return NRGBD_ERR_BAD_ARG; }
+  if (k == "conv_math") {            // 0: exact fp32 (CUDA cores); 1: tcgen05 3xTF32; 2: tcgen05 split-fp16 pairs
+    if (value < 0 || value > 2) { nrgbd_set_error("conv_math must be 0 (fp32), 1 (tf32x3) or 2 (f16x3)"); return NRGBD_ERR_BAD_ARG; }
     drop_graphs(e); e->conv_math = value; return NRGBD_OK;
   }
   nrgbd_set_error("nrgbd_kvnet_set_option: unknown option '%s'", key);

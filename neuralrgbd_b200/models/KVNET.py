@@ -236,9 +236,10 @@ class KVNET(nn.Module):
             ent = self._engine(H, W, V, dev)
             self._sync_params(ent, dev)
             if ent['conv_math'] != self.conv_math:
-                if self.conv_math not in ('fp32', 'tf32x3'):
-                    raise ValueError("conv_math must be 'fp32' or 'tf32x3'")
-                check(L.nrgbd_kvnet_set_option(ent['h'], b'conv_math', 1 if self.conv_math == 'tf32x3' else 0))
+                modes = {'fp32': 0, 'tf32x3': 1, 'f16x3': 2}
+                if self.conv_math not in modes:
+                    raise ValueError("conv_math must be 'fp32', 'tf32x3' or 'f16x3'")
+                check(L.nrgbd_kvnet_set_option(ent['h'], b'conv_math', modes[self.conv_math]))
                 ent['conv_math'] = self.conv_math
             self._set_camera(ent, 0, cam=self.cam_intrinsics)
             prior = None

@@ -8,8 +8,8 @@ from neuralrgbd_b200 import _lib
 from tests.conftest import ROOT
 
 
-def _declared():
-    src = open(os.path.join(ROOT, 'include', 'nrgbd.h')).read()
+def _declared(header='nrgbd.h'):
+    src = open(os.path.join(ROOT, 'include', header)).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(nrgbd_[a-z0-9_]+)\s*\(', src)))
 
@@ -24,6 +24,20 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_ctypes_table_matches_header():
     assert sorted(_lib.SIGNATURES.keys()) == _declared()
+
+
+def test_dev_knobs_live_in_their_own_header():
+    """Development probes / A-B switches are not part of the product ABI: separate header, separate
+    ctypes table, exported by the library, and no environment variable is read by the native code."""
+    dev = _declared('nrgbd_dev.h')
+    assert sorted(_lib.DEV_SIGNATURES.keys()) == dev and len(dev) >= 4
+    assert not set(dev) & set(_declared())
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in dev:
+        assert hasattr(L, n)
+    import glob
+    for f in glob.glob(os.path.join(ROOT, 'neuralrgbd_b200', 'csrc', '*')):
+        assert 'getenv' not in open(f).read(), '%s reads the environment' % f
 
 
 def test_version_and_error_string_without_gpu():

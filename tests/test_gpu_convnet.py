@@ -126,7 +126,7 @@ def build_model(c, cam):
     return m.to(dev)
 
 
-@pytest.mark.parametrize('conv_math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('conv_math', ['fp32', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('name', cases.KVNET_CASES)
 def test_kvnet_forward_streaming_vs_reference(golden, name, conv_math):
     """KVNET.forward first-window + steady branches and the streaming test() loop against the
@@ -184,7 +184,7 @@ def test_kvnet_forward_streaming_vs_reference(golden, name, conv_math):
     assert torch.equal(a[3], b[3]) and torch.equal(a[0], b[0])
 
 
-@pytest.mark.parametrize('conv_math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('conv_math', ['fp32', 'tf32x3', 'f16x3'])
 def test_kvnet_vs_oracle_first_window(conv_math):
     """Engine vs the numpy oracle on a fresh seed (not in the fixtures)."""
     c = cases.kvnet_case('kvnet_256x320_d8')

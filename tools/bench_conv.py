@@ -14,7 +14,7 @@ from neuralrgbd_b200 import _lib, convops        # noqa: E402
 from neuralrgbd_b200._lib import ptr, check      # noqa: E402
 
 dev = torch.device('cuda:0')
-L = _lib.lib()
+L = _lib.dev_lib()
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)     # noqa: E731
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -41,6 +41,8 @@ SHAPES = [  # name, N, D, H, W, Cin, Cout, k(kd), stride, pad, dil
     ('rnet conv1 96->96 @1/2', 1, 1, 240, 320, 96, 96, 3, 1, 1, 1),
     ('rnet conv2_2 64->64 @1', 1, 1, 480, 640, 64, 64, 3, 1, 1, 1),
     ('knet 64->64 3d (D=64)', 1, 64, 120, 160, 64, 64, 3, 1, 1, 1),
+    ('rnet conv2 67->67 @1', 1, 1, 480, 640, 67, 67, 3, 1, 1, 1),
+    ('rnet conv0 320->320 (D=256) @1/4 1080p', 1, 1, 270, 480, 320, 320, 3, 1, 1, 1),
 ]
 
 
@@ -52,6 +54,8 @@ def main():
         if a.startswith('dev='):
             st_, fl_ = a[4:].split(',')
             L.nrgbd_conv_tc_set_dev(int(st_), int(fl_))
+        if a.startswith('h2flags='):
+            L.nrgbd_dev_conv_h2_set_flags(int(a[8:]))
     only = [a[5:] for a in sys.argv[1:] if a.startswith('only=')]
     for name, N, D, H, W, Cin, Cout, k, s, p, d in SHAPES:
         if only and not any(o in name for o in only):
@@ -84,11 +88,34 @@ def main():
             check(L.nrgbd_conv_nhwc_tc2(ptr(x), N, D, H, W, Cs, Cs, ptr(wh), ptr(wl), None, Cout, convops.pad_to(Cout, 16), kd, k, k,
                                         s, p, d, ptr(y3), Ho, Wo, Cso, 0, 0, ctypes.c_void_p(stats.data_ptr()), st()))
         y3 = torch.zeros_like(y)
-        t_simt = timeit(simt); t_split = timeit(split); t_tc = timeit(tc); t_tc2 = timeit(tc2)
+        y4 = torch.zeros_like(y)
+        wp2, cin_p2, cout_p2, bn2 = convops.pack_weight_h2(w)
+        ph = torch.empty(x.shape, device=dev, dtype=torch.float16); pl = torch.empty_like(ph)
+
+        def split_h2():
+            check(L.nrgbd_split_f16_pair(ptr(x), x.numel(), ptr(ph), ptr(pl), st()))
+
+        def h2():
+            check(L.nrgbd_conv_nhwc_h2(ptr(ph), ptr(pl), N, D, H, W, cin_p2, Cs, ptr(wp2), None, Cout, cout_p2, bn2, kd, k, k, s, p, d,
+                                       ptr(y4), Ho, Wo, Cso, 0, 0, ctypes.c_void_p(stats.data_ptr()), st()))
+        quick = 'quick' in sys.argv
+        def safe(fn, iters=10):
+            try:
+                return timeit(fn, iters)
+            except _lib.NrgbdError:
+                return float('nan')
+        if 'h2only' in sys.argv:
+            t_h2 = safe(h2)
+            print(json.dumps(dict(layer=name, h2_us=t_h2, h2_tflops=flops / t_h2 / 1e6)), flush=True)
+            continue
+        t_simt = safe(simt, 3 if quick else 10); t_split = safe(split); t_tc = safe(tc, 3 if quick else 10); t_tc2 = safe(tc2)
+        t_split_h2 = safe(split_h2); t_h2 = safe(h2)
         err = float((y - y2).abs().max() / y.abs().max())
         rec = dict(layer=name, gflop=flops / 1e9, simt_us=t_simt, simt_tflops=flops / t_simt / 1e6, split_us=t_split, tc_us=t_tc,
                    tc_tflops=flops / t_tc / 1e6, tc_vs_simt_relerr=err, tc2_us=t_tc2,
-                   tc2_tflops=flops / t_tc2 / 1e6, tc2_vs_simt_relerr=float((y - y3).abs().max() / y.abs().max()))
+                   tc2_tflops=flops / t_tc2 / 1e6, tc2_vs_simt_relerr=float((y - y3).abs().max() / y.abs().max()),
+                   h2_us=t_h2, h2_split_us=t_split_h2, h2_tflops=flops / t_h2 / 1e6,
+                   h2_vs_simt_relerr=float((y - y4).abs().max() / y.abs().max()))
         out.append(rec)
         print(json.dumps(rec), flush=True)
     os.makedirs('gpurun_out', exist_ok=True)

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neuralrgbd_b200 import _lib
 from neuralrgbd_b200._lib import check
-L = _lib.lib(); dev = torch.device('cuda:0')
+L = _lib.dev_lib(); dev = torch.device('cuda:0')
 out = torch.zeros(2, dtype=torch.int64, device=dev)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 n = 1200

@@ -5,7 +5,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neuralrgbd_b200 import _lib, convops
 from neuralrgbd_b200._lib import ptr, check
-dev = torch.device('cuda:0'); L = _lib.lib()
+dev = torch.device('cuda:0'); L = _lib.dev_lib()
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 N, D, H, W, Cin, Cout = [int(a) for a in sys.argv[1:7]]
 flags = int(sys.argv[7]) if len(sys.argv) > 7 else 0

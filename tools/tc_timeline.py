@@ -7,7 +7,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neuralrgbd_b200 import _lib, convops
 from neuralrgbd_b200._lib import ptr, check
-dev = torch.device('cuda:0'); L = _lib.lib()
+dev = torch.device('cuda:0'); L = _lib.dev_lib()
 st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 N, H, W, Cin, Cout, k = 5, 120, 160, int(sys.argv[1]) if len(sys.argv) > 1 else 64, int(sys.argv[2]) if len(sys.argv) > 2 else 64, 3
 x = torch.randn((N, 1, H, W, Cin), device=dev); xh = torch.empty_like(x); xl = torch.empty_like(x)
