@@ -1,28 +1,38 @@
 #!/usr/bin/env python
 """bench.py - depth frames/s of the plane-sweep DPV hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1..c5] [--impl engine|reference|reference-gpu]
 
-Workload (config.workload): BASELINE.json configs[1] - ScanNet-shaped 640x480 frames, 64 depth
-planes, 4 source views, D-Net DPV (feature CNN + fused plane sweep + log-softmax) + R-Net
-up-sampling = the first-window branch of KVNET.forward (models/KVNET.py:93-143), i.e. SURVEY
-§8(d) config C2. One step = one depth frame. Synthetic seeded frames / poses / random-init
-weights of the reference architecture (no datasets or checkpoints offline).
+Workloads = BASELINE.json configs. `--config` picks one; the default c2 is the configuration the metric is
+quoted on (the driver's BENCH / SCALE runs use it), the others write the same JSON line for their shape:
+  c1  single 320x256 reference + 1 source pair, 32 planes, C = 67: warping.homography.est_swp_volume_v4 only
+  c2  640x480, 64 planes, 4 source views, D-Net DPV + R-Net = first-window KVNET.forward           (default)
+  c3  c2's shape, full KVNet (D-Net + K-Net Bayesian filter + 2x R-Net + DPV propagation), streaming 30-frame window
+  c4  1248x376 (the reference CNN rejects 1242x375), 128 KITTI planes, full KVNet streaming, frame chunks sharded over ranks
+  c5  1920x1080, 256 planes, 8 source views, first-window KVNET.forward (the 1/2/4/8-GPU throughput sweep)
+One step = one depth frame (c1: one cost volume). Synthetic seeded frames / poses / random-init weights of the reference
+architecture (no datasets or checkpoints offline).
 
-value  : whole-job frames/s with the window already resident in HBM (engine C ABI, device ptrs).
-e2e    : the same metric through the public Python surface (KVNET.forward + depth regression)
-         with pinned HOST buffers: H2D of the 5-frame window + poses and D2H of the full-resolution
-         expected-depth and confidence maps inside the timed region, every step.
-roofline: the conv implicit-GEMM kernels (dominant: ~76 % of the step; conv_tc2_kernel, tcgen05 3xTF32) timed with CUDA
-         events on the launching stream in eager frames run right after the timed graph replays; algorithmic fp32
-         FLOPs / time against the measured bf16 tensor peak of MEASURED_PEAKS.json (the MMA rate is 3x the
-         algorithmic rate). The fused plane-sweep kernel's HBM fraction is reported beside it
-         (config.sweep).
-cpu_baseline / --impl reference: oracle/torch_port.py, the CPU torch port of the reference's path (same ATen
-         ops; the reference itself cannot travel to the GPU box), on all host cores.
+value  : whole-job frames/s with the inputs already resident in HBM (engine C ABI, device pointers).
+e2e    : the same metric through the public Python surface with pinned HOST buffers inside the timed region, every step:
+         c1/c2/c5 upload the float window + poses and read back the full-resolution depth + confidence maps;
+         c3/c4 stream ONE decoded uint8 frame per step into the resident FrameWindow (mdataloader mirror, SURVEY f-4),
+         run the reference-named inference step (test_utils.test_KVNet.test: forward + DPV propagation) and read back the
+         depth map and the confidence map (export_res mirror, f-2).
+roofline: the dominant kernel family (conv_h2_kernel, tcgen05 kind::f16 on split-fp16 pairs) timed with CUDA events around
+         every launch on the launching stream, in eager frames with ONE frame in flight run right after the timed region;
+         the frames/s of that same regime is reported next to it (roofline.regime). achieved = algorithmic fp32 FLOPs /
+         kernel time against the measured bf16 tensor peak (MEASURED_PEAKS.json; the kernel issues 3 f16 MMAs per
+         product: its MMA rate is 3x the algorithmic rate). The geometry kernels' HBM fractions are listed in config.hbm_kernels.
+cpu_baseline / --impl reference: the UNMODIFIED reference (baseline/_ref, copied by baseline/fetch_reference.py) through its
+         own models.KVNET.KVNET.forward / test_utils.test_KVNet.test on the host cores (the 4-line .cuda() shim of SURVEY
+         8c; kind "reference"); oracle/torch_port.py (kind "port") only when baseline/_ref is absent.
+--impl reference-gpu: the same unmodified reference, unshimmed, eager ATen/cuDNN on the same B200 (SURVEY 8d ii), with
+         cudnn.benchmark as test_KVNet.py:10 sets it; also records its TF32-default vs fp32 deviation (the noise floor
+         the reference itself has on this GPU).
 
-N > 1 (torchrun): one process per GPU, frames shard naturally (independent windows), weights are
-broadcast once over NCCL, no per-frame collective; value = N*K frames / max-over-ranks time.
+N > 1 (torchrun): one process per GPU; frames (c1, c2, c5) / trajectory chunks (c3, c4) shard across ranks, weights are
+broadcast once over NCCL, no per-frame collective; value = all ranks' frames / max-over-ranks time.
 """
 import argparse
 import contextlib
@@ -40,9 +50,26 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_CODE = os.path.join(ROOT, 'baseline', '_ref', 'code')
 
-H_IMG, W_IMG, D_PLANES, V_SRC = 480, 640, 64, 4
-WORKLOAD = 'scannet640x480_d64_v4_dnet_dpv_plus_rnet (BASELINE.json configs[1]; SURVEY C2)'
+SCANNET = dict(fx=585.0, fy=585.0, cx=320.0, cy=240.0, d=(0.1, 5.0))          # DSO/cam_info_7scenes.mat, test_KVNet.py ScanNet planes
+CONFIGS = {
+    'c1': dict(kind='sweep', h=256, w=320, V=1, D=32, C=67, intr=SCANNET,
+               workload='pair320x256_d32_c67_plane_sweep_cost (BASELINE.json configs[0]; SURVEY C1)',
+               metric='plane-sweep cost volumes/sec at 320x256x32-plane x1-view (C=67)'),
+    'c2': dict(kind='first', H=480, W=640, D=64, V=4, r=2, intr=SCANNET, inflight=3,
+               workload='scannet640x480_d64_v4_dnet_dpv_plus_rnet (BASELINE.json configs[1]; SURVEY C2)',
+               metric='depth frames/sec at 640x480x64-plane x4-view'),
+    'c3': dict(kind='stream', H=480, W=640, D=64, V=4, r=2, intr=SCANNET, n_stream=30,
+               workload='scannet640x480_d64_v4_full_kvnet_stream30 (BASELINE.json configs[2]; SURVEY C3)',
+               metric='depth frames/sec at 640x480x64-plane x4-view, full KVNet (D-Net + K-Net + 2x R-Net + propagation), streaming'),
+    'c4': dict(kind='stream', H=376, W=1248, D=128, V=4, r=2, intr=dict(fx=721.5377, fy=721.5377, cx=624.0, cy=188.0, d=(1.0, 60.0)), n_stream=12,
+               workload='kitti1248x376_d128_v4_full_kvnet_stream (BASELINE.json configs[3]; 1242x375 is rejected by the reference CNN; SURVEY C4)',
+               metric='depth frames/sec at 1248x376x128-plane x4-view, full KVNet, streaming'),
+    'c5': dict(kind='first', H=1080, W=1920, D=256, V=8, r=4, intr=dict(fx=1755.0, fy=1755.0, cx=960.0, cy=540.0, d=(0.1, 5.0)), inflight=1,
+               workload='synthetic1920x1080_d256_v8_dnet_dpv_plus_rnet (BASELINE.json configs[4]; SURVEY C5)',
+               metric='depth frames/sec at 1920x1080x256-plane x8-view'),
+}
 
 
 def read_peaks():
@@ -74,7 +101,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
@@ -90,31 +117,44 @@ class ClockSampler(threading.Thread):
 
 
 def conv_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch (mean over the 70 conv launches of one frame) from the
-    committed ncu capture profiles/r1b_conv_dram_traffic.json (bytes); None if the file is missing."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch (mean over the conv launches of one c2 frame) from the ncu
+    capture of this round's kernels, profiles/r2_conv_dram_traffic.json; None if the file is missing."""
     try:
-        return float(json.load(open(os.path.join(ROOT, 'profiles', 'r1b_conv_dram_traffic.json')))['traffic_bytes_per_launch'])
+        return float(json.load(open(os.path.join(ROOT, 'profiles', 'r2_conv_dram_traffic.json')))['traffic_bytes_per_launch'])
     except Exception:
         return None
 
 
-def make_windows(n_windows, seed=7):
-    """n_windows seeded 5-frame windows: frames [V+1,3,H,W] (sources then reference, basic.py:245) and
-    relative poses [V,4,4]."""
+def make_video(cfg, n_frames, seed):
     from neuralrgbd_b200 import synth
-    frames, rng = synth.video(seed, n_windows + 4, H_IMG, W_IMG)
-    exts = synth.camera_track(rng, n_windows + 4)
+    frames, rng = synth.video(seed, n_frames, cfg['H'], cfg['W'])
+    exts = synth.camera_track(rng, n_frames)
+    return frames, exts
+
+
+def make_windows(cfg, n_windows, seed=7):
+    """n_windows seeded windows: frames [V+1,3,H,W] (sources then reference, basic.py:245) and relative poses [V,4,4]."""
+    from neuralrgbd_b200 import synth
+    r = cfg['r']
+    frames, exts = make_video(cfg, n_windows + 2 * r, seed)
     wins = []
     for i in range(n_windows):
-        poses, idx = synth.window_rel_poses(exts, 2 + i, 2)
-        f = np.stack([frames[j] for j in idx] + [frames[2 + i]])
+        poses, idx = synth.window_rel_poses(exts, r + i, r)
+        f = np.stack([frames[j] for j in idx] + [frames[r + i]])
         wins.append((np.ascontiguousarray(f, np.float32), np.ascontiguousarray(poses, np.float32)))
     return wins
 
 
-# ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores
-# ----------------------------------------------------------------------------------------------
+def cam_of(cfg, make_cam, quarter=True):
+    i = cfg['intr']
+    if cfg['kind'] == 'sweep':
+        return make_cam(i['fx'], i['fy'], i['cx'], i['cy'], [cfg['w'], cfg['h']])
+    return make_cam(i['fx'], i['fy'], i['cx'], i['cy'], [cfg['W'] // 4, cfg['H'] // 4])
+
+
+# ==============================================================================================
+# reference arms: the unmodified reference (baseline/_ref) on the host cores / on the same GPU
+# ==============================================================================================
 def pick_cpu_threads():
     """Thread count for the CPU arm: the fastest of {all cores, 64, 32, 16, 8} on a short calibration over the three conv
     shapes that dominate the frame (on many-core hosts torch's intra-op pool oversubscribes: 128 threads ran this path 6x
@@ -122,7 +162,7 @@ def pick_cpu_threads():
     import torch
     import torch.nn.functional as F
     n_all = os.cpu_count() or 1
-    cands = sorted({c for c in (n_all, 64, 32, 16, 8) if c <= n_all})      # ascending: a hopeless large count is cut short
+    cands = sorted({c for c in (n_all, 64, 32, 16, 8) if c <= n_all})
     work = [(torch.randn(5, 64, 120, 160), torch.randn(64, 64, 3, 3)), (torch.randn(5, 128, 120, 160), torch.randn(128, 128, 3, 3)),
             (torch.randn(5, 32, 240, 320), torch.randn(32, 32, 3, 3))]
     best, best_t = cands[0], None
@@ -132,7 +172,7 @@ def pick_cpu_threads():
         for x, w in work:
             F.conv2d(x, w, padding=1)
         if best_t is not None and time.perf_counter() - t0 > 4 * best_t:
-            continue                                   # hopeless (oversubscribed): do not spend more time on it
+            continue
         t0 = time.perf_counter()
         for _ in range(2):
             for x, w in work:
@@ -144,62 +184,171 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_frame_seconds(n_frames=1):
-    """Time the CPU torch port of the reference path (oracle/torch_port.py: the same ATen ops in the
-    same order as the reference, bit-identical to its recorded outputs) on whole depth frames of the
-    bench workload (same shapes, seeded inputs and weights), all host threads."""
+def reference_runner(cfg, on_gpu):
+    """-> (step(i) -> seconds, description). Drives the unmodified reference (or, without baseline/_ref, the torch port)."""
     import torch
-    from oracle import planesweep_oracle as O, torch_port as TP
     from neuralrgbd_b200 import arch, synth
-    cpu_frame_seconds.threads = pick_cpu_threads()
-    cam = O.make_cam_intrinsics(585., 585., 320., 240., [W_IMG // 4, H_IMG // 4])
-    sd = TP._P(arch.synth_state_dict(5, 64, D_PLANES, 2, 64))
-    d = synth.d_candidates(D_PLANES)
-    wins = make_windows(n_frames)
-    ts = []
-    for f, poses in wins:
-        t0 = time.perf_counter()
-        ref, bv, dep = TP.kvnet_first_window(sd, f[-1:], f[None, :-1], poses[None], cam, d, 10.)
-        ts.append(time.perf_counter() - t0)
-        assert np.isfinite(dep).all()
-    return ts
+    from oracle import planesweep_oracle as O
+    have_ref = os.path.isdir(REF_CODE)
+    scale = 1.0
+    crop = None
+    if cfg['kind'] != 'sweep' and not on_gpu and cfg['H'] * cfg['W'] * cfg['D'] > 1248 * 376 * 128:
+        # bounded CPU sample of the biggest configuration: a centred half-size crop (1/4 of the pixels), fps scaled by 1/4
+        crop = dict(cfg, H=cfg['H'] // 2 // 4 * 4, W=cfg['W'] // 2 // 4 * 4)
+        crop['intr'] = dict(cfg['intr'], cx=crop['W'] / 2.0, cy=crop['H'] / 2.0)
+        scale = (crop['H'] * crop['W']) / float(cfg['H'] * cfg['W'])
+        cfg = crop
+    i = cfg['intr']
+    d = synth.d_candidates(cfg['D'], i['d'][0], i['d'][1])
+    camn = cam_of(cfg, O.make_cam_intrinsics)
+    cam = dict(camn, unit_ray_array_2D=torch.from_numpy(camn['unit_ray_array_2D']), intrinsic_M_cuda=torch.from_numpy(camn['intrinsic_M_cuda']))
+    dev = torch.device('cuda:0') if on_gpu else torch.device('cpu')
+    if not on_gpu and have_ref:                      # SURVEY 8c: the reference hard-codes .cuda()
+        torch.Tensor.cuda = lambda s, *a, **k: s
+        torch.nn.Module.cuda = lambda s, *a, **k: s
+        torch.cuda.current_device = lambda: 0
+        torch.Tensor.get_device = lambda s: 0
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)      # noqa: E731
+    if cfg['kind'] == 'sweep':
+        from tests import cases
+        c = cases.sweep_case('c1_320x256_v1_d32_c67')
+        if have_ref:
+            sys.path.insert(0, REF_CODE)
+            import warping.homography as wh                     # reference
+            args = (T(c['ref']), T(c['src']), c['d'], T(c['R']), T(c['t']), cam, c['sigma'])
+
+            def step(k):
+                t0 = time.perf_counter()
+                out = wh.est_swp_volume_v4(*args)
+                if on_gpu:
+                    torch.cuda.synchronize()
+                assert torch.isfinite(out).all()
+                return time.perf_counter() - t0
+            return step, 'unmodified reference warping.homography.est_swp_volume_v4 (baseline/_ref)', 'reference', 1.0
+        from oracle import torch_port as TP
+
+        def step(k):
+            t0 = time.perf_counter()
+            TP.est_swp_volume_v4(torch.from_numpy(c['ref']), torch.from_numpy(c['src']), c['d'], torch.from_numpy(c['R']), torch.from_numpy(c['t']), camn, c['sigma'])
+            return time.perf_counter() - t0
+        return step, 'CPU torch port of est_swp_volume_v4 (baseline/_ref absent)', 'port', 1.0
+    r = cfg['r']
+    sd = arch.synth_state_dict(5, 64, cfg['D'], r, 64)
+    n_frames = 2 * r + 4
+    frames, exts = make_video(cfg, n_frames, 7)
+    if not have_ref:
+        if cfg['kind'] != 'first' or on_gpu:
+            raise RuntimeError('baseline/_ref is not present: only the first-window CPU port is available')
+        from oracle import torch_port as TP
+        P = TP._P(sd)
+
+        def step(k):
+            poses, idx = synth.window_rel_poses(exts, r + k % 3, r)
+            f = np.stack([frames[j] for j in idx] + [frames[r + k % 3]])
+            t0 = time.perf_counter()
+            TP.kvnet_first_window(P, f[-1:], f[None, :-1], poses[None], camn, d, 10.)
+            return time.perf_counter() - t0
+        return step, 'CPU torch port of the reference path (oracle/torch_port.py; baseline/_ref absent)', 'port', scale
+    sys.path.insert(0, REF_CODE)
+    import models.KVNET as m_kvnet                              # reference
+    import test_utils.test_KVNet as ref_step                    # reference
+    if on_gpu:
+        import torch.backends.cudnn as cudnn
+        cudnn.benchmark = True                                  # test_KVNet.py:10
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = m_kvnet.KVNET(feature_dim=64, cam_intrinsics=cam, d_candi=d, sigma_soft_max=10., KVNet_feature_dim=64,
+                              d_upsample_ratio_KV_net=None, t_win_r=r, if_refined=True)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model = torch.nn.DataParallel(model)
+    model.cuda()
+    state = {'bv': None}
+
+    def window(k):
+        poses, idx = synth.window_rel_poses(exts, r + k, r)
+        Ref = [{'img': torch.from_numpy(frames[r + k][None])}]
+        Src = [[{'img': torch.from_numpy(frames[j][None])} for j in idx]]
+        return Ref, Src, T(poses[None])
+
+    if cfg['kind'] == 'first':
+        def step(k):
+            Ref, Src, poses = window(k % 3)
+            t0 = time.perf_counter()
+            out, _ = ref_step.test(model, d, [cam], r, Ref, Src, poses, None, R_net=True)
+            if on_gpu:
+                torch.cuda.synchronize()
+            assert torch.isfinite(out).all()
+            return time.perf_counter() - t0
+    else:
+        def step(k):
+            if state['bv'] is None:                              # untimed first window seeds the recursion
+                Ref, Src, poses = window(0)
+                _, state['bv'] = ref_step.test(model, d, [cam], r, Ref, Src, poses, None, R_net=True)
+            Ref, Src, poses = window(1 + k % 3)
+            t0 = time.perf_counter()
+            out, bv = ref_step.test(model, d, [cam], r, Ref, Src, poses, state['bv'], R_net=True)
+            if on_gpu:
+                torch.cuda.synchronize()
+            assert torch.isfinite(out).all()
+            state['bv'] = bv
+            return time.perf_counter() - t0
+    what = 'unmodified reference (baseline/_ref): models.KVNET.KVNET.forward + resample_vol_cuda through its own test_utils.test_KVNet.test'
+    if crop is not None:
+        what += ', on a centred %dx%d crop (%.3f of the pixels; frames/s scaled by that factor)' % (cfg['W'], cfg['H'], scale)
+    return step, what, 'reference', scale
 
 
-def run_reference(args):
+def run_reference(args, cfg, on_gpu):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_warm = 1 if args.warmup > 0 else 0
-    n = max(1, min(args.steps, 3))           # bounded: each frame costs seconds of CPU time
-    ts = cpu_frame_seconds(n_warm + n)[n_warm:]
-    cores = cpu_frame_seconds.threads
+    import torch
+    cores = 0
+    if not on_gpu:
+        cores = pick_cpu_threads()
+    step, what, kind, scale = reference_runner(cfg, on_gpu)
+    n_warm = (2 if on_gpu else 1) if args.warmup > 0 else 0
+    cap = args.steps if on_gpu else min(args.steps, 3 if cfg['kind'] != 'sweep' else 10)      # CPU frames cost seconds each: bounded sample
+    with torch.no_grad():
+        for k in range(n_warm):
+            step(k)
+        ts = [step(n_warm + k) for k in range(max(1, cap))]
     sec = float(np.mean(ts))
-    val = 1.0 / sec
+    val = scale / sec
     line = {
-        'impl': 'reference', 'metric': 'depth frames/sec at 640x480x64-plane x4-view', 'value': val, 'unit': 'frames/s',
-        'n_gpus': args.gpus, 'steps': len(ts), 'warmup': n_warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG]},
-        'cpu_baseline': {'value': val, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': 'CPU torch port of the reference path (same ATen ops, bit-identical to the reference fixtures), '
-                                   '%d whole 640x480 frame(s) after %d warm-up, torch.set_num_threads(%d) (fastest of a calibration over {all=%d,64,32,16,8})' % (len(ts), n_warm, cores, os.cpu_count())},
+        'impl': 'reference-gpu' if on_gpu else 'reference', 'metric': cfg['metric'], 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': len(ts), 'warmup': n_warm, 'ms_per_step': sec * 1e3 / scale, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (cuDNN/cuBLAS TF32 defaults of torch, as the reference runs)' if on_gpu else 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['workload'], 'name': args.config},
         'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if on_gpu:
+        line['config']['what'] = what + '; eager ATen/cuDNN on cuda:0, cudnn.benchmark=True, frames uploaded inside the timed step by the reference itself'
+    else:
+        line['cpu_baseline'] = {'value': val, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                                'sample': '%s; %d step(s) after %d warm-up, torch.set_num_threads(%d) (fastest of a calibration over {all=%d,64,32,16,8})'
+                                          % (what, len(ts), n_warm, cores, os.cpu_count())}
     _emit(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------------------------
+def cpu_baseline_subprocess(args):
+    """The CPU arm as a child process (the reference needs torch's .cuda() patched away, which must not happen in the process
+    that drives the GPU). Returns the child's cpu_baseline object or an error note."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', args.config, '--steps', '1', '--warmup', '1'],
+                           capture_output=True, text=True, timeout=1500, env=dict(os.environ, RANK='0', WORLD_SIZE='1'))
+        line = [l for l in r.stdout.splitlines() if l.startswith('{')]
+        return json.loads(line[-1])['cpu_baseline'] if line else {'error': (r.stderr or 'no output')[-300:]}
+    except Exception as e:          # noqa: BLE001
+        return {'error': repr(e)[:300]}
+
+
+# ==============================================================================================
 # the engine arm
-# ----------------------------------------------------------------------------------------------
-def run_engine(args):
+# ==============================================================================================
+def dist_setup():
     import torch
     import torch.distributed as dist
-    from neuralrgbd_b200 import _lib, arch, camera, sharding, synth
-    from neuralrgbd_b200._lib import ptr, check
-    from neuralrgbd_b200.models.KVNET import KVNET
-    from neuralrgbd_b200.mutils import misc
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -207,227 +356,423 @@ def run_engine(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if 'NRGBD_NCCL_DEBUG' in os.environ:
-            os.environ['NCCL_DEBUG'] = os.environ['NRGBD_NCCL_DEBUG']
-        else:
-            os.environ.pop('NCCL_DEBUG', None)        # any level >= VERSION prints a banner
-        dist.init_process_group('nccl', device_id=dev)
+        dist.init_process_group('nccl', device_id=dev)          # NCCL_DEBUG is left alone: fd 1 points at stderr until the result line
+    return world, rank, local, dev
+
+
+def max_ms(ms, world, dev):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_sweep(args, cfg):
+    """c1: the fused plane-sweep cost kernel through warping.homography.est_swp_volume_v4 (public mirror)."""
+    import torch
+    import torch.distributed as dist
+    import neuralrgbd_b200.warping.homography as Hm
+    from neuralrgbd_b200 import _lib, camera
+    from tests import cases
+    world, rank, local, dev = dist_setup()
     L = _lib.lib()
     peaks = read_peaks()
     K, Wm = args.steps, args.warmup
+    c = cases.sweep_case('c1_320x256_v1_d32_c67')
+    i = cfg['intr']
+    cam = camera.make_cam_intrinsics(i['fx'], i['fy'], i['cx'], i['cy'], [cfg['w'], cfg['h']])
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)      # noqa: E731
+    ref, src, R, t = T(c['ref']), T(c['src']), T(c['R']), T(c['t'])
+    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (c['ref'], c['src'], c['R'], c['t'])]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host_out = torch.empty((1, cfg['D'], cfg['h'], cfg['w'])).pin_memory()
+    for _ in range(Wm):
+        Hm.est_swp_volume_v4(ref, src, c['d'], R, t, cam, c['sigma'])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
 
-    cam = camera.make_cam_intrinsics(585., 585., 320., 240., [W_IMG // 4, H_IMG // 4])
-    d = synth.d_candidates(D_PLANES)
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = KVNET(64, cam, d, 10., 64, None, t_win_r=2)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    L.nrgbd_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        flush.zero_()
+        Hm.est_swp_volume_v4(ref, src, c['d'], R, t, cam, c['sigma'])
+    e1.record()
+    barrier()
+    launches = int(L.nrgbd_launch_count())
+    ms = max_ms(e0.elapsed_time(e1), world, dev)
+    # kernel-only time of the sweep (events around each call, no flush in between the event pair)
+    ks = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); Hm.est_swp_volume_v4(ref, src, c['d'], R, t, cam, c['sigma']); b.record(); torch.cuda.synchronize()
+        ks.append(a.elapsed_time(b))
+    barrier()
+    e0.record()
+    for _ in range(K):
+        flush.zero_()
+        dr, ds, dR, dt = [p.to(dev, non_blocking=True) for p in pin]
+        out = Hm.est_swp_volume_v4(dr, ds, c['d'], dR, dt, cam, c['sigma'])
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = max_ms(e0.elapsed_time(e1), world, dev)
+    sampler.stop = True
+    if rank == 0:
+        hw = cfg['h'] * cfg['w']
+        alg_bytes = ((1 + cfg['V']) * cfg['C'] + cfg['D'] + 3) * hw * 4.0
+        call_ms = float(np.median(ks))
+        gbs = alg_bytes / (call_ms * 1e-3) / 1e9
+        line = {
+            'metric': cfg['metric'], 'value': world * K / (ms * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': cfg['workload'], 'name': args.config, 'l2': 'explicit 256 MiB flush write before every step (inside the timed region)',
+                       'parallelism': 'dp%d (independent pairs)' % world},
+            'e2e': {'value': world * K / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': sum(p.numel() * 4 for p in pin),
+                    'd2h_bytes_per_step': host_out.numel() * 4},
+            'gpu_launches': launches, 'clocks': sampler.summary(),
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'traffic': None,
+                         'kernel': 'est_swp_volume_v4 mirror = pack_features x2 + sweep set-up + plane_sweep kernel + transpose, %.1f us per call '
+                                   '(CUDA events around the call, median of 10); algorithmic bytes (1+V) C hw 4 + D hw 4 + 3 hw 4 = %.1f MB. At C = 67 the '
+                                   'kernel is gather / FFMA bound, not HBM bound (SURVEY 8d)' % (call_ms * 1e3, alg_bytes / 1e6),
+                         'peak_source': peaks['source'] + ', HBM copy'},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline_subprocess(args)
+        _emit(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_engine(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from neuralrgbd_b200 import _lib, arch, camera, sharding, synth
+    from neuralrgbd_b200._lib import ptr, check
+    from neuralrgbd_b200.models.KVNET import KVNET
+    from neuralrgbd_b200.mutils import misc
+    from neuralrgbd_b200.mdataloader import m_preprocess
+    from neuralrgbd_b200.test_utils import test_KVNet as step_mod
+    from neuralrgbd_b200.test_utils import export_res
+
+    world, rank, local, dev = dist_setup()
+    L = _lib.lib()
+    peaks = read_peaks()
+    K, Wm = args.steps, args.warmup
+    H_IMG, W_IMG, D_PLANES, V_SRC, R_WIN = cfg['H'], cfg['W'], cfg['D'], cfg['V'], cfg['r']
+    stream_mode = cfg['kind'] == 'stream'
+    ii = cfg['intr']
+    cam = camera.make_cam_intrinsics(ii['fx'], ii['fy'], ii['cx'], ii['cy'], [W_IMG // 4, H_IMG // 4])
+    d = synth.d_candidates(D_PLANES, ii['d'][0], ii['d'][1])
+
+    def new_model():
+        with contextlib.redirect_stdout(io.StringIO()):
+            return KVNET(64, cam, d, 10., 64, None, t_win_r=R_WIN)
+    model = new_model()
     # random-init weights of the reference architecture: rank 0 generates, NCCL broadcasts (weights only)
     if rank == 0:
-        sd = arch.synth_state_dict(5, 64, D_PLANES, 2, 64)
+        sd = arch.synth_state_dict(5, 64, D_PLANES, R_WIN, 64)
         model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     model = model.to(dev)
     model.conv_math = args.conv_math
     sharding.broadcast_module(model, src=0)
-
-    n_win = 4
-    wins = make_windows(n_win, seed=7 + rank)           # every rank owns its own windows (frames shard naturally)
-    dev_frames = [torch.from_numpy(f).to(dev) for f, _ in wins]
-    dev_poses = [torch.from_numpy(p).to(dev) for _, p in wins]
-    pin_frames = [torch.from_numpy(f).pin_memory() for f, _ in wins]
-    pin_poses = [torch.from_numpy(p).pin_memory() for _, p in wins]
-    h2d_bytes = pin_frames[0].numel() * 4 + pin_poses[0].numel() * 4
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    out_ref = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
-    out_bv = torch.empty((D_PLANES, H_IMG // 4, W_IMG // 4), device=dev)
-    out_dep = torch.empty((H_IMG // 4, W_IMG // 4), device=dev)
-    d2h_bytes = 2 * H_IMG * W_IMG * 4
-
-    # one API-level call per engine creates it, syncs weights and the camera. `inflight` independent
-    # engines (own buffers, shared read-only weights) run consecutive frames on their own streams so that
-    # one frame's kernels fill the other's tail waves (750 conv tiles = 5.07 waves on 148 SMs).
-    inflight = max(1, args.inflight)
-    models = [model]
-    for _ in range(inflight - 1):
-        with contextlib.redirect_stdout(io.StringIO()):
-            m2 = KVNET(64, cam, d, 10., 64, None, t_win_r=2)
-        m2.load_state_dict(model.state_dict())
-        m2 = m2.to(dev); m2.conv_math = args.conv_math
-        models.append(m2)
-    streams = [torch.cuda.current_stream()] + [torch.cuda.Stream(device=dev) for _ in range(inflight - 1)]
-    hnds = []
-    for m_, s_ in zip(models, streams):
-        with torch.cuda.stream(s_), torch.no_grad():
-            m_(dev_frames[0][-1:], dev_frames[0][None, :-1], dev_poses[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
-        hnds.append(m_._engine(H_IMG, W_IMG, V_SRC, dev)['h'])
-    torch.cuda.synchronize()
-    hnd = hnds[0]
-    stream = streams[0]
-    outs = [(torch.empty_like(out_ref), torch.empty_like(out_bv), torch.empty_like(out_dep)) for _ in range(inflight)]
-
-    def step_resident(i):
-        k = i % inflight
-        sk = streams[k]
-        with torch.cuda.stream(sk):
-            if k == 0:
-                flush.zero_()
-            check(L.nrgbd_kvnet_forward(hnds[k], ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(outs[k][0]), None,
-                                        ptr(outs[k][1]), None, ptr(outs[k][2]), None, ctypes.c_void_p(sk.cuda_stream)))
+    h, w = H_IMG // 4, W_IMG // 4
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM ----------------
-    # untimed priming: every (engine, window) pointer tuple gets its CUDA graph captured before any timing
-    n_prime = inflight * n_win // math.gcd(inflight, n_win)
-    for i in range(n_prime):
-        step_resident(i)
-    torch.cuda.synchronize()
-    for i in range(Wm):
-        step_resident(i)
     ms_c, wk_c, n_c = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    L.nrgbd_reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for s_ in streams[1:]:
-        s_.wait_stream(stream)
-    for i in range(K):
-        step_resident(Wm + i)
-    for s_ in streams[1:]:
-        stream.wait_stream(s_)
-    e1.record(stream)
-    barrier()
-    launches = int(L.nrgbd_launch_count())
-    ms_total = e0.elapsed_time(e1)
-    # per-kernel CUDA-event profile: the timed steps are CUDA-graph replays (one launch per frame), which cannot
-    # carry per-kernel events, so the same step is run P_PROF more times eagerly, back to back on the same
-    # stream right after the timed region, with the engine's event brackets around its conv / sweep launches
-    P_PROF = 4
+    inflight = 1
+    if not stream_mode:
+        # ------------------------------------------------------------------ first-window frames (c2, c5)
+        n_win = 4 if H_IMG * W_IMG <= 640 * 480 else 2
+        wins = make_windows(cfg, n_win, seed=7 + rank)           # every rank owns its own windows (frames shard naturally)
+        dev_frames = [torch.from_numpy(f).to(dev) for f, _ in wins]
+        dev_poses = [torch.from_numpy(p).to(dev) for _, p in wins]
+        pin_frames = [torch.from_numpy(f).pin_memory() for f, _ in wins]
+        pin_poses = [torch.from_numpy(p).pin_memory() for _, p in wins]
+        h2d_bytes = pin_frames[0].numel() * 4 + pin_poses[0].numel() * 4
+        d2h_bytes = 2 * H_IMG * W_IMG * 4
+        # `inflight` independent engines (own buffers, shared read-only weights) run consecutive frames on their own
+        # streams so that one frame's kernels fill the other's tail waves
+        inflight = max(1, args.inflight if args.inflight > 0 else cfg.get('inflight', 1))
+        models = [model]
+        for _ in range(inflight - 1):
+            m2 = new_model()
+            m2.load_state_dict(model.state_dict())
+            m2 = m2.to(dev); m2.conv_math = args.conv_math
+            models.append(m2)
+        streams = [torch.cuda.current_stream()] + [torch.cuda.Stream(device=dev) for _ in range(inflight - 1)]
+        hnds = []
+        for m_, s_ in zip(models, streams):
+            with torch.cuda.stream(s_), torch.no_grad():
+                m_(dev_frames[0][-1:], dev_frames[0][None, :-1], dev_poses[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+            hnds.append(m_._engine(H_IMG, W_IMG, V_SRC, dev)['h'])
+        torch.cuda.synchronize()
+        hnd, stream = hnds[0], streams[0]
+        outs = [(torch.empty((D_PLANES, H_IMG, W_IMG), device=dev), torch.empty((D_PLANES, h, w), device=dev), torch.empty((h, w), device=dev))
+                for _ in range(inflight)]
+
+        def step_resident(i):
+            k = i % inflight
+            sk = streams[k]
+            with torch.cuda.stream(sk):
+                if k == 0:
+                    flush.zero_()
+                check(L.nrgbd_kvnet_forward(hnds[k], ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(outs[k][0]), None,
+                                            ptr(outs[k][1]), None, ptr(outs[k][2]), None, ctypes.c_void_p(sk.cuda_stream)))
+        n_prime = inflight * n_win // math.gcd(inflight, n_win)
+        for i in range(n_prime):          # untimed priming: every (engine, window) pointer tuple gets its CUDA graph captured
+            step_resident(i)
+        torch.cuda.synchronize()
+        for i in range(Wm):
+            step_resident(i)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        L.nrgbd_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s_ in streams[1:]:
+            s_.wait_stream(stream)
+        for i in range(K):
+            step_resident(Wm + i)
+        for s_ in streams[1:]:
+            stream.wait_stream(s_)
+        e1.record(stream)
+        barrier()
+        launches = int(L.nrgbd_launch_count())
+        ms_value = max_ms(e0.elapsed_time(e1), world, dev)
+
+        def eager_frame(i):
+            flush.zero_()
+            check(L.nrgbd_kvnet_forward(hnd, ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(outs[0][0]), None,
+                                        ptr(outs[0][1]), None, ptr(outs[0][2]), None, ctypes.c_void_p(stream.cuda_stream)))
+    else:
+        # ------------------------------------------------------------------ streaming full KVNet (c3, c4)
+        n_stream = cfg['n_stream']
+        frames, exts = make_video(cfg, n_stream + 2 * R_WIN, seed=7 + rank)      # every rank streams its own trajectory chunk
+        dev_f = [torch.from_numpy(f[None]).to(dev) for f in frames]
+        u8 = [np.ascontiguousarray(np.clip((f.transpose(1, 2, 0) * 0.226 + 0.45) * 255.0, 0, 255).astype(np.uint8)) for f in frames]
+        pin_u8 = [torch.from_numpy(a).pin_memory() for a in u8]
+        win_list, pose_list, next_list = [], [], []
+        for i in range(n_stream):
+            poses, idx = synth.window_rel_poses(exts, R_WIN + i, R_WIN)
+            win_list.append(torch.cat([dev_f[j] for j in idx] + [dev_f[R_WIN + i]], 0).contiguous())
+            pose_list.append(torch.from_numpy(np.ascontiguousarray(poses, np.float32)).to(dev))
+            next_list.append(torch.from_numpy(np.linalg.inv(poses[R_WIN].astype(np.float64)).astype(np.float32)).to(dev))     # inverse of the (t+1) pose
+        h2d_bytes = pin_u8[0].numel() + V_SRC * 64
+        d2h_bytes = 2 * H_IMG * W_IMG * 4
+        with torch.no_grad():
+            model(win_list[0][-1:], win_list[0][None, :-1], pose_list[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+        ent = model._engine(H_IMG, W_IMG, V_SRC, dev)
+        model._set_camera(ent, 1, cam=cam)             # per-call intrinsics (K-Net image warp, propagation): the same camera here
+        hnd = ent['h']
+        stream = torch.cuda.current_stream()
+        st_ptr = ctypes.c_void_p(stream.cuda_stream)
+        o_ref = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
+        o_dpv = torch.empty((D_PLANES, h, w), device=dev)
+        o_dep = torch.empty((h, w), device=dev)
+        priors = [torch.empty((D_PLANES, h, w), device=dev) for _ in range(2)]
+
+        def stream_step(i, have_prior):
+            """One depth frame of the stream on resident inputs: forward (K-Net when a prior exists) + propagation."""
+            k = i % n_stream
+            flush.zero_()
+            if k == 0 or not have_prior:
+                check(L.nrgbd_kvnet_forward(hnd, ptr(win_list[k]), ptr(pose_list[k]), None, ptr(o_ref), None, None, None, ptr(o_dep), None, st_ptr))
+            else:
+                check(L.nrgbd_kvnet_forward(hnd, ptr(win_list[k]), ptr(pose_list[k]), ptr(priors[i % 2]), None, ptr(o_ref), None, ptr(o_dpv),
+                                            ptr(o_dep), None, st_ptr))
+            check(L.nrgbd_kvnet_propagate(hnd, None, ptr(next_list[k]), ptr(priors[(i + 1) % 2]), st_ptr))
+        stream_step(0, False)
+        for i in range(1, 3 + Wm):                     # warm-up: first window + steady-state graph capture
+            stream_step(i, True)
+        torch.cuda.synchronize()
+        if rank == 0:
+            sampler.start()
+        barrier()
+        L.nrgbd_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        base = 3 + Wm
+        for i in range(K):
+            stream_step(base + i, True)                # a 30-frame window: the recursion restarts (first-window frame) every n_stream frames
+        e1.record(stream)
+        barrier()
+        launches = int(L.nrgbd_launch_count())
+        ms_value = max_ms(e0.elapsed_time(e1), world, dev)
+
+        def eager_frame(i):
+            stream_step(1 + i % (n_stream - 1), True)
+
+    # ---------------- roofline pass: per-kernel CUDA events, eager, ONE frame in flight, right after the timed region -----------
+    P_PROF = 4 if H_IMG * W_IMG * D_PLANES <= 1248 * 376 * 128 else 2
     check(L.nrgbd_kvnet_set_option(hnd, b'profile', 1))
-    L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))   # clear
-    L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))
+    for cat in (0, 1, 2):
+        L.nrgbd_kvnet_profile_read(hnd, cat, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c))   # clear
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record(stream)
     for i in range(P_PROF):
-        flush.zero_()
-        check(L.nrgbd_kvnet_forward(hnd, ptr(dev_frames[i % n_win]), ptr(dev_poses[i % n_win]), None, ptr(outs[0][0]), None,
-                                    ptr(outs[0][1]), None, ptr(outs[0][2]), None, ctypes.c_void_p(stream.cuda_stream)))
+        eager_frame(i)
     p1.record(stream)
     torch.cuda.synchronize()
     prof_ms_total = p0.elapsed_time(p1)
-    if args.layer_table and rank == 0:
-        # per-shape conv table of the profiling pass (ms per frame, TFLOP/s algorithmic) for DESIGN.md / profiles/
+    layer_rows = None
+    if rank == 0:
         buf = ctypes.create_string_buffer(1 << 16)
         check(L.nrgbd_kvnet_profile_table(hnd, 0, buf, len(buf)))
-        rows = []
-        for line in buf.value.decode().splitlines():
-            tag, n, ms, work = line.split(';')
-            rows.append({'layer': tag, 'launches_per_frame': int(n) // P_PROF, 'ms_per_frame': float(ms) / P_PROF,
-                         'algorithmic_tflops': float(work) / (float(ms) * 1e-3) / 1e12})
-        rows.sort(key=lambda r: -r['ms_per_frame'])
-        with open(args.layer_table, 'w') as f:
-            json.dump({'note': 'conv launches of one 640x480 D=64 V=4 frame, CUDA events around each launch in %d eager frames' % P_PROF,
-                       'frame_ms_eager': prof_ms_total / P_PROF, 'layers': rows}, f, indent=1)
+        layer_rows = []
+        for ln in buf.value.decode().splitlines():
+            tag, n, ms, work = ln.split(';')
+            layer_rows.append({'layer': tag, 'launches_per_frame': int(n) / P_PROF, 'ms_per_frame': float(ms) / P_PROF,
+                               'algorithmic_tflops': float(work) / (float(ms) * 1e-3) / 1e12})
+        layer_rows.sort(key=lambda r_: -r_['ms_per_frame'])
+        if args.layer_table:
+            with open(args.layer_table, 'w') as f:
+                json.dump({'note': 'conv launches of one %s frame (%s), CUDA events around each launch in %d eager frames, one frame in flight'
+                                   % (args.config, args.conv_math, P_PROF), 'frame_ms_eager': prof_ms_total / P_PROF, 'layers': layer_rows}, f, indent=1)
     check(L.nrgbd_kvnet_profile_read(hnd, 0, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
     conv_ms, conv_flops, conv_n = ms_c.value, wk_c.value, n_c.value
     check(L.nrgbd_kvnet_profile_read(hnd, 1, ctypes.byref(ms_c), ctypes.byref(wk_c), ctypes.byref(n_c)))
     sw_ms, sw_bytes, sw_n = ms_c.value, wk_c.value, n_c.value
     check(L.nrgbd_kvnet_set_option(hnd, b'profile', 0))
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * K / (ms_max * 1e-3)
+    value = world * K / (ms_value * 1e-3)
 
-    # ---------------- e2e: public Python surface, pinned host buffers ----------------
-    # The same pipelining a video application uses: `inflight` model instances, each on its own stream
-    # with its own pinned staging buffers. Every step still does its H2D of the 5-frame window + poses, the
-    # forward through KVNET.forward + depth regression, and the D2H of the full-resolution depth and
-    # confidence maps; the host consumes a step's result when that stream is next reused (or at the end).
-    h_depth = [torch.empty((1, H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
-    h_conf = [torch.empty((1, H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
-    done_ev = [None] * inflight
-    consumed = [0]
+    # ---------------- e2e: public Python surface, pinned host buffers inside the timed region ----------------
+    if not stream_mode:
+        h_depth = [torch.empty((1, H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
+        h_conf = [torch.empty((1, H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
+        done_ev = [None] * inflight
 
-    def consume(k):
-        if done_ev[k] is not None:
-            done_ev[k].synchronize()              # the user reads the depth map on the host
-            consumed[0] += float(h_depth[k][0, 0, 0]) * 0.0 + 1
+        def consume(k):
+            if done_ev[k] is not None:
+                done_ev[k].synchronize()              # the user reads the depth map on the host
 
-    def step_e2e(i):
-        k = i % inflight
-        consume(k)
-        sk = streams[k]
-        with torch.cuda.stream(sk):
-            if k == 0:
-                flush.zero_()
-            f = pin_frames[i % n_win].to(dev, non_blocking=True)
-            p = pin_poses[i % n_win].to(dev, non_blocking=True)
-            with torch.no_grad():
-                out = models[k](f[-1:], f[None, :-1], p[None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
-                dep, conf = misc.depth_val_regression(out[0], d, BV_log=True, return_conf=True)
-            h_depth[k].copy_(dep, non_blocking=True)
-            h_conf[k].copy_(conf, non_blocking=True)
-            ev = torch.cuda.Event(); ev.record(sk); done_ev[k] = ev
-    for i in range(n_prime + Wm):          # priming (graph capture per pointer tuple) + warm-up, untimed
-        step_e2e(i)
-    for k in range(inflight):
-        consume(k); done_ev[k] = None
-    barrier()
-    e0.record(stream)
-    for s_ in streams[1:]:
-        s_.wait_stream(stream)
-    for i in range(K):
-        step_e2e(Wm + i)
-    for k in range(inflight):
-        consume(k)
-    for s_ in streams[1:]:
-        stream.wait_stream(s_)
-    e1.record(stream)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * K / (float(t.item()) * 1e-3)
+        def step_e2e(i):
+            k = i % inflight
+            consume(k)
+            sk = streams[k]
+            with torch.cuda.stream(sk):
+                if k == 0:
+                    flush.zero_()
+                f = pin_frames[i % n_win].to(dev, non_blocking=True)
+                p = pin_poses[i % n_win].to(dev, non_blocking=True)
+                with torch.no_grad():
+                    out = models[k](f[-1:], f[None, :-1], p[None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+                    dep, conf = misc.depth_val_regression(out[0], d, BV_log=True, return_conf=True)
+                h_depth[k].copy_(dep, non_blocking=True)
+                h_conf[k].copy_(conf, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(sk); done_ev[k] = ev
+        for i in range(n_prime + Wm):
+            step_e2e(i)
+        for k in range(inflight):
+            consume(k); done_ev[k] = None
+        barrier()
+        e0.record(stream)
+        for s_ in streams[1:]:
+            s_.wait_stream(stream)
+        for i in range(K):
+            step_e2e(Wm + i)
+        for k in range(inflight):
+            consume(k)
+        for s_ in streams[1:]:
+            stream.wait_stream(s_)
+        e1.record(stream)
+        barrier()
+        host_depth = h_depth[0]
+    else:
+        # the reference's streaming loop (test_KVNet.py:190-250) on the mirrors: one new decoded frame per step
+        fw = m_preprocess.FrameWindow(t_win_r=R_WIN, img_size=None, device=dev)
+        h_depth = torch.empty((H_IMG, W_IMG)).pin_memory()
+        h_conf = torch.empty((H_IMG, W_IMG)).pin_memory()
+        state = {'bv': None, 'pos': 0}
+
+        def step_e2e():
+            flush.zero_()
+            if state['pos'] == 0 or state['pos'] >= len(pin_u8):          # new trajectory chunk: refill the window, restart the recursion
+                fw.frames.clear(); state['bv'] = None
+                for j in range(2 * R_WIN):
+                    fw.push(pin_u8[j], exts[j])
+                state['pos'] = 2 * R_WIN
+            k = state['pos']; state['pos'] += 1
+            fw.push(pin_u8[k], exts[k])                    # H2D: ONE decoded uint8 frame; the other 2r frames of the window are resident
+            fds = fw.frame_dicts()
+            ref_d, src_d = fds[R_WIN], [fd for j, fd in enumerate(fds) if j != R_WIN]
+            inv_ref = np.linalg.inv(ref_d['extM'])
+            poses = np.stack([fd['extM'].dot(inv_ref) for fd in src_d]).astype(np.float32)      # warping.homography.get_rel_extrinsicM
+            poses_t = torch.from_numpy(poses[None]).to(dev, non_blocking=True)
+            dmap, bv = step_mod.test(model, d, [cam], R_WIN, [ref_d], [src_d], poses_t, state['bv'], R_net=True)
+            maps = export_res.depth_conf_maps(dmap, d, want_float=True, want_u16=False)
+            h_depth.copy_(maps['dmap'], non_blocking=True)
+            h_conf.copy_(maps['conf'], non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the user reads the maps on the host before the next frame arrives
+            state['bv'] = bv
+        for i in range(3 + Wm):
+            step_e2e()
+        barrier()
+        e0.record(stream)
+        for i in range(K):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        host_depth = h_depth
+    e2e_value = world * K / (max_ms(e0.elapsed_time(e1), world, dev) * 1e-3)
     sampler.stop = True
-    host_depth = h_depth[0]
     assert np.isfinite(host_depth.numpy()).all()
 
     if rank == 0:
         conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         sweep_gbs = sw_bytes / (sw_ms * 1e-3) / 1e9 if sw_ms > 0 else 0.0
         peak_tf = peaks['bf16_sustained']       # kernels timed inside a long step -> sustained figure
+        kname = {'f16x3': 'conv_h2_kernel (tcgen05 kind::f16 on split-fp16 operand pairs, halo tile, persistent CTAs; algorithmic fp32 FLOPs, the MMA rate is 3x this)',
+                 'tf32x3': 'conv_tc2_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)',
+                 'fp32': 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)'}[args.conv_math]
+        dtype = {'f16x3': 'f32 (split-fp16 pair products: 22-bit significands, fp32 accumulate)', 'tf32x3': 'f32 (3xTF32 error-compensated products, fp32 accumulate)',
+                 'fp32': 'f32'}[args.conv_math]
         line = {
-            'metric': 'depth frames/sec at 640x480x64-plane x4-view', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
-            'steps': K, 'warmup': Wm, 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32' if args.conv_math == 'fp32' else 'f32 (3xTF32 error-compensated tensor-core products, fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'conv_math': args.conv_math, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG], 'parallelism': 'dp%d (frames sharded, weights NCCL-broadcast once)' % world,
-                       'l2': 'explicit 256 MiB flush write before every %s step (inside the timed region)' % ('second' if inflight == 2 else '%d-th' % inflight if inflight > 2 else ''),
+            'metric': cfg['metric'], 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms_value / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
+            'config': {'workload': cfg['workload'], 'name': args.config, 'conv_math': args.conv_math, 'planes': D_PLANES, 'views': V_SRC, 'frame': [H_IMG, W_IMG],
+                       'parallelism': 'dp%d (%s sharded, weights NCCL-broadcast once)' % (world, 'trajectory chunks' if stream_mode else 'frames'),
+                       'l2': 'explicit 256 MiB flush write before every %s step (inside the timed region)' % ('' if inflight == 1 else '%d-th' % inflight),
                        'frames_in_flight': inflight,
                        'weights': 'random init of the reference architecture (arch.synth_state_dict seed 5)',
-                       'sweep': {'avg_us': 1e3 * sw_ms / max(sw_n, 1), 'algorithmic_GBps': sweep_gbs, 'frac_of_hbm_peak': sweep_gbs / peaks['hbm_gbs'],
-                                 'note': 'fused plane-sweep cost kernel incl. setup launch; C=67 is L1/FFMA bound, not HBM bound (SURVEY 8d)'},
+                       'hbm_kernels': {'plane_sweep': {'avg_us': 1e3 * sw_ms / max(sw_n, 1), 'algorithmic_GBps': sweep_gbs, 'frac_of_hbm_peak': sweep_gbs / peaks['hbm_gbs'],
+                                                       'note': 'fused plane-sweep (+ log-softmax) kernel; at C = 67 it is gather / FFMA bound, not HBM bound (SURVEY 8d)'}},
                        'conv_share_of_step': conv_ms / prof_ms_total if prof_ms_total > 0 else None,
                        'cuda_graph': 'each frame is one cudaGraphLaunch (captured per I/O pointer tuple after an eager warm-up)'},
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes},
             'gpu_launches': launches,
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'achieved': conv_tflops, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': conv_tflops / peak_tf,
-                         'traffic': conv_traffic_per_launch() if args.conv_math == 'tf32x3' else None, 'kernel': ('conv_tc2_kernel (tcgen05 3xTF32 implicit GEMM; algorithmic fp32 FLOPs, the MMA rate is 3x this)' if args.conv_math == 'tf32x3' else 'conv_igemm_kernel<128,{32,64}> (fp32 FFMA implicit GEMM)') + ', %d launches/step, avg %.1f us (CUDA events around every conv launch in %d eager frames run right after the timed graph replays)' % (conv_n // P_PROF, 1e3 * conv_ms / max(conv_n, 1), P_PROF),
-                         'traffic_note': 'bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the 70 conv launches of one frame, ncu capture profiles/r1b_conv_dram_traffic.json (2.46 GB read + 0.28 GB written per frame)',
+                         'traffic': conv_traffic_per_launch() if (args.conv_math == 'f16x3' and args.config == 'c2') else None,
+                         'kernel': kname + ', %d launches/step, avg %.1f us' % (conv_n // P_PROF, 1e3 * conv_ms / max(conv_n, 1)),
+                         'regime': {'what': 'CUDA events around every conv launch in %d eager frames, ONE frame in flight, run right after the timed region' % P_PROF,
+                                    'frames_per_s_in_this_regime': 1e3 * P_PROF / prof_ms_total, 'frame_ms': prof_ms_total / P_PROF},
+                         'traffic_note': 'bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the conv launches of one c2 frame, ncu capture of this '
+                                         "round's kernels (profiles/r2_conv_dram_traffic.json)",
                          'peak_source': peaks['source'] + ', sustained bf16'},
         }
-        # cpu baseline: bounded sample of the same workload through the oracle port (rank 0, N = 1 only)
+        if layer_rows:
+            line['config']['top_conv_layers'] = [{'layer': r_['layer'], 'n': r_['launches_per_frame'], 'ms': round(r_['ms_per_frame'], 4),
+                                                  'tflops': round(r_['algorithmic_tflops'], 1)} for r_ in layer_rows[:4]]
         if world == 1 and not args.no_cpu_baseline:
-            ts = cpu_frame_seconds(2)[1:]
-            line['cpu_baseline'] = {'value': 1.0 / float(np.mean(ts)), 'unit': 'frames/s', 'cores': cpu_frame_seconds.threads, 'kind': 'port',
-                                    'sample': 'CPU torch port of the reference path (same ATen ops, bit-identical to the reference '
-                                              'fixtures), 1 whole 640x480 frame after 1 warm-up frame, torch.set_num_threads(%d) '
-                                              '(fastest of a calibration over {all=%d,64,32,16,8})' % (cpu_frame_seconds.threads, os.cpu_count())}
+            line['cpu_baseline'] = cpu_baseline_subprocess(args)
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -441,25 +786,31 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference', 'reference-gpu'])
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--layer-table', default=None, help='write the per-shape conv table of the profiling pass to this JSON file')
-    ap.add_argument('--inflight', type=int, default=3, help='independent frames in flight on separate streams (resident-value loop)')
-    ap.add_argument('--conv-math', default='tf32x3', choices=['fp32', 'tf32x3'],
-                    help='fp32: exact CUDA-core FFMA implicit GEMM; tf32x3: tcgen05 error-compensated 3xTF32 (default)')
+    ap.add_argument('--layer-table', default=None, help='write the per-shape conv table of the roofline pass to this JSON file')
+    ap.add_argument('--inflight', type=int, default=0, help='independent frames in flight on separate streams (first-window configs; 0 = the config default)')
+    ap.add_argument('--conv-math', default='f16x3', choices=['fp32', 'tf32x3', 'f16x3'],
+                    help='f16x3: tcgen05 kind::f16 on split-fp16 pairs (default); tf32x3: tcgen05 3xTF32; fp32: exact CUDA-core FFMA implicit GEMM')
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == 'engine' else args.warmup
-    # stdout carries exactly one JSON line: anything a library prints there meanwhile (e.g. NCCL's version banner)
-    # is sent to stderr by pointing fd 1 at fd 2 until the result line is written to the real stdout
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (e.g. NCCL's version banner with
+    # NCCL_DEBUG set) is sent to stderr by pointing fd 1 at fd 2 until the result line is written to the real stdout
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     global _emit
     _emit = lambda text: os.write(real_stdout, (text + '\n').encode())      # noqa: E731
     if args.impl == 'reference':
-        run_reference(args)
+        run_reference(args, cfg, on_gpu=False)
+    elif args.impl == 'reference-gpu':
+        run_reference(args, cfg, on_gpu=True)
+    elif cfg['kind'] == 'sweep':
+        run_sweep(args, cfg)
     else:
-        run_engine(args)
+        run_engine(args, cfg)
 
 
 if __name__ == '__main__':

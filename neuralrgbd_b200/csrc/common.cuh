@@ -1,6 +1,7 @@
 // Shared helpers for the nrgbd sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -102,4 +103,25 @@ __device__ __forceinline__ void plane_project(float t1x, float t1y, float t1z, f
   float gy = __fdiv_rn(__fsub_rn(py, cy), cy);
   ix = unnormalize(gx, Wf);
   iy = unnormalize(gy, Hf);
+}
+
+
+// ---------------------------------------------------------------------------
+// Split-fp16 operand pair of the second-generation tensor-core convolution (csrc/conv_f16.cu):
+// a = hi + lo * 2^-11 with hi = RN_f16(a), lo = RN_f16((a - hi) * 2^11); saturating at the fp16 range.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void nrgbd_split_pair(float a, __half& hi, __half& lo) {
+  const float c = fminf(fmaxf(a, -65504.f), 65504.f);
+  hi = __float2half_rn(c);
+  const float r = (c - __half2float(hi)) * 2048.f;           // exact difference, exact power-of-two scale
+  lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+}
+__device__ __forceinline__ void nrgbd_split_pair4(const float* o, uint2& hi, uint2& lo) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) nrgbd_split_pair(o[k], h[k], l[k]);
+  hi.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+  hi.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+  lo.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+  lo.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
 }

@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(256)
 bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ stats, double count,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                       float* __restrict__ run_mean, float* __restrict__ run_var, float momentum,
-                      const float* __restrict__ res, int relu, long long n4, int Cs, int C, float* __restrict__ y) {
+                      const float* __restrict__ res, int relu, long long n4, int Cs, int C, float* __restrict__ y,
+                      uint2* __restrict__ y_hi, uint2* __restrict__ y_lo) {
   __shared__ float s_scale[512], s_shift[512];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double mean = stats[c] / count;
@@ -330,7 +331,12 @@ bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ st
       float4 r = reinterpret_cast<const float4*>(res)[i];
       o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
     }
-    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (y) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (y_hi) {                      // the consumer is an f16-pair convolution: emit its operand planes in the same pass
+      uint2 h, l;
+      nrgbd_split_pair4(o, h, l);
+      y_hi[i] = h; y_lo[i] = l;
+    }
   }
 }
 
@@ -460,7 +466,23 @@ int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, cons
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   bn_apply_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                         n4, Cs, C, y);
+                                                         n4, Cs, C, y, nullptr, nullptr);
+  NRGBD_COUNT(1);
+  NRGBD_LAUNCH_CHECK();
+  return NRGBD_OK;
+}
+
+// Same pass, additionally (or only: y may be NULL) writing the result as the split-fp16 operand pair of the f16-pair
+// convolution that consumes it (nrgbd_conv_nhwc_h2): y_hi / y_lo are half tensors with x's layout.
+int nrgbd_bn_apply_stats_pair(const float* x, const double* stats, double count, const float* gamma, const float* beta, float eps,
+                              float* run_mean, float* run_var, float momentum, const float* res, int relu, long long n_pos, int Cs,
+                              int C, float* y, void* y_hi, void* y_lo, cudaStream_t st) {
+  NRGBD_REQUIRE(x && stats && gamma && beta && y_hi && y_lo && Cs % 4 == 0 && C <= Cs && C <= 512 && n_pos > 0 && count > 0, "bad arguments");
+  long long n4 = n_pos * Cs / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_apply_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
+                                                         n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo));
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;

@@ -521,12 +521,7 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_pair(float a, __half& hi, __half& lo) {
-  const float c = fminf(fmaxf(a, -H_MAX), H_MAX);
-  hi = __float2half_rn(c);
-  const float r = (c - __half2float(hi)) * LO_SCALE;           // exact difference, exact power-of-two scale
-  lo = __float2half_rn(fminf(fmaxf(r, -H_MAX), H_MAX));
-}
+__device__ __forceinline__ void split_pair(float a, __half& hi, __half& lo) { nrgbd_split_pair(a, hi, lo); }
 
 // fp32 [n] -> hi / lo halves [n]
 __global__ void __launch_bounds__(256)

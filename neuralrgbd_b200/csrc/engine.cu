@@ -337,8 +337,11 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
 
 // Conv (no bias) + BatchNorm(batch statistics) [+ ReLU] [+ residual]; BN applied in place.
 // `pre` is the Sequential(Conv, BN) prefix: weights pre.0.weight, pre.1.{weight,bias,running_*}.
+// out_use (f16-pair mode only): 0 = the result is read as fp32 only; 1 = also by a convolution (the BatchNorm pass emits the
+// split-fp16 operand planes together with the fp32 tensor); 2 = ONLY by a convolution (no fp32 copy is written: y.p keeps
+// the raw conv output and must not be read as an activation).
 Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k, int stride, int pad, int dil,
-           bool relu, const Act* res) {
+           bool relu, const Act* res, int out_use = 0) {
   int p = (kd == 1 && dil > 1) ? dil : pad;          // psm_submodule.convbn :13
   Act y = conv(e, x, pre + ".0.weight", Cout, kd, k, stride, p, dil, nullptr, false, true);
   float* g = param(e, pre + ".1.weight");
@@ -346,6 +349,17 @@ Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k
   float* rm = e->bn_update_running ? param_opt(e, pre + ".1.running_mean") : nullptr;
   float* rv = e->bn_update_running ? param_opt(e, pre + ".1.running_var") : nullptr;
   if (e->rc) return y;
+  if (out_use && use_h2(e, y)) {
+    PairBuf pb;
+    pb.hi = e->pool.acquire((size_t)y.floats() * 2);
+    pb.lo = e->pool.acquire((size_t)y.floats() * 2);
+    if (!pb.hi || !pb.lo) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return y; }
+    ENG_CALL(e, nrgbd_bn_apply_stats_pair(y.p, e->stats, (double)y.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
+                                          0.1f, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, out_use == 2 ? nullptr : y.p,
+                                          pb.hi, pb.lo, (nrgbd_stream_t)e->st));
+    e->pairs[y.p] = pb;
+    return y;
+  }
   ENG_CALL(e, nrgbd_bn_apply_stats(y.p, e->stats, (double)y.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
                                    0.1f, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, y.p, (nrgbd_stream_t)e->st));
   return y;
@@ -367,7 +381,7 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
   const bool fused = e->fuse_bn && (planes >= 64 || e->fuse_bn >= 2) && takes_tc2(e, x, planes) && takes_tc2(e, probe, planes);
   Act t;
   if (fused) t = conv(e, x, pre + ".conv1.0.0.weight", planes, 1, 3, stride, p1, dil, nullptr, false, true, nullptr, 0, -1, e->stats_b);
-  else t = convbn(e, x, pre + ".conv1.0", planes, 1, 3, stride, 1, dil, true, nullptr);
+  else t = convbn(e, x, pre + ".conv1.0", planes, 1, 3, stride, 1, dil, true, nullptr, 2);
   Act sc; const Act* res = &x;
   if (down) {
     // downsample = Sequential(Conv2d 1x1 stride, BatchNorm2d) :125-131 -> names downsample.0 / downsample.1
@@ -398,7 +412,7 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
                                        0.1f, res->p, 0, o.pos(), o.Cs, o.C, o.p, (nrgbd_stream_t)e->st));
     }
   } else {
-    o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res);
+    o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res, 1);
   }
   release(e, t);
   if (down) release(e, sc);
@@ -447,9 +461,9 @@ void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
                                        0.1f, nullptr, 1, c.pos(), c.Cs, c.C, c.p, (nrgbd_stream_t)e->st));
     }
   } else {
-    Act a = convbn(e, x0, P + ".firstconv.0", 32, 1, 3, 2, 1, 1, true, nullptr);
-    Act b = convbn(e, a, P + ".firstconv.2", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, a);
-    c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr); release(e, b);
+    Act a = convbn(e, x0, P + ".firstconv.0", 32, 1, 3, 2, 1, 1, true, nullptr, 2);
+    Act b = convbn(e, a, P + ".firstconv.2", 32, 1, 3, 1, 1, 1, true, nullptr, 2); release(e, a);
+    c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr, 1); release(e, b);
   }
   Act l1 = make_layer(e, c, true, P + ".layer1", 32, 3, 1, 1, false);
   Act raw = make_layer(e, l1, false, P + ".layer2", 64, 16, 2, 1, true);
@@ -491,7 +505,7 @@ void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
   }
   for (int bi = 0; bi < 4; ++bi) release(e, pools[bi]);
   release(e, raw); release(e, skip);
-  Act lc = convbn(e, cat, P + ".lastconv.0", 128, 1, 3, 1, 1, 1, true, nullptr);
+  Act lc = convbn(e, cat, P + ".lastconv.0", 128, 1, 3, 1, 1, 1, true, nullptr, 2);
   release(e, cat);
   feat_out = conv(e, lc, P + ".lastconv.2.weight", e->F, 1, 1, 1, 0, 1, nullptr, false, false, nullptr, 0, pad4(e->F));   // dense: the sweep's wide layout
   release(e, lc);
@@ -572,19 +586,19 @@ void r_net(Eng* e, const float* bv_hwd, const float* feat_ref, int feat_Cs, cons
 // models/basic.py:113-139 on a channels-last volume [D][h][w][CK] -> gain [D][hw] (DHW, Cs = 1)
 Act kv_net(Eng* e, const Act& vol) {
   const int f = e->KF;
-  auto cb = [&](const Act& x, const std::string& name, bool relu, const Act* res) {
-    return convbn(e, x, name, f, 3, 3, 1, 1, 1, relu, res);
+  auto cb = [&](const Act& x, const std::string& name, bool relu, const Act* res, int out_use) {
+    return convbn(e, x, name, f, 3, 3, 1, 1, 1, relu, res, out_use);
   };
-  Act a = cb(vol, "kv_net.dres0.0", true, nullptr);
-  Act c = cb(a, "kv_net.dres0.2", true, nullptr); release(e, a);
+  Act a = cb(vol, "kv_net.dres0.0", true, nullptr, 2);
+  Act c = cb(a, "kv_net.dres0.2", true, nullptr, 1); release(e, a);      // also the residual of dres1
   for (int i = 1; i <= 4; ++i) {
     std::string p = "kv_net.dres" + std::to_string(i);
-    Act r = cb(c, p + ".0", true, nullptr);
-    Act o = cb(r, p + ".2", false, &c);
+    Act r = cb(c, p + ".0", true, nullptr, 2);
+    Act o = cb(r, p + ".2", false, &c, i < 4 ? 1 : 2);                     // dres4's output feeds classify.0 only
     release(e, r); release(e, c);
     c = o;
   }
-  Act o = cb(c, "kv_net.classify.0", true, nullptr); release(e, c);
+  Act o = cb(c, "kv_net.classify.0", true, nullptr, 2); release(e, c);
   Act gain = conv(e, o, "kv_net.classify.2.weight", 1, 3, 3, 1, 1, 1, nullptr, false, false, nullptr, 0, 1);
   release(e, o);
   return gain;

@@ -91,7 +91,9 @@ class KVNET(nn.Module):
         self.if_upsample_d = if_upsample_d
         self.cam_intrinsics = cam_intrinsics          # captured at construction: used by D-Net (KVNET.py:64-67)
         self.feat_dist = 'L2'                         # basic.py:146 default, never overridden by KVNET
-        self.conv_math = 'tf32x3'                     # 'tf32x3' (tcgen05 tensor cores, error-compensated; default) | 'fp32' (exact CUDA-core FFMA)
+        # convolution arithmetic: 'f16x3' (default; tcgen05 kind::f16 on split-fp16 operand pairs, 22-bit products, fp32 accumulate -
+        # the fastest AND the closest to the reference of the tensor paths), 'tf32x3' (tcgen05 3xTF32), 'fp32' (exact CUDA-core FFMA)
+        self.conv_math = 'f16x3'
 
         D = len(d_candi)
         gen = torch.Generator().manual_seed(0)
