@@ -66,6 +66,16 @@ int nrgbd_plane_sweep_cost_packed(const float* ref_wide, const float* ref_narrow
                                   const float* d_planes, float cx, float cy, float sigma, int metric,
                                   float* ws, float* cost_hwd, nrgbd_stream_t stream);
 
+/* The D-Net head after the feature CNN in ONE kernel (models/basic.py:270-300): the cost above, then
+ * BV = log_softmax(-cost) [h*w][D], expected depth sum_d exp(BV) d (mutils/misc.py:532-548) and confidence max_d exp(BV);
+ * any of cost_hwd / bv_hwd / depth / conf may be NULL (the cost volume then never reaches memory). */
+int nrgbd_plane_sweep_dpv_packed(const float* ref_wide, const float* ref_narrow, const float* src_wide,
+                                 const float* src_narrow, int Cw, int Cn, int V, int D, int h, int w,
+                                 const float* K, const float* R, const float* t, const float* rays,
+                                 const float* d_planes, float cx, float cy, float sigma, int metric,
+                                 float* ws, float* cost_hwd, float* bv_hwd, float* depth, float* conf,
+                                 nrgbd_stream_t stream);
+
 /* ---- a7: image warp to volume --------------------------------------------------------------
  * replaces warping/homography.py:234-280 warp_img_feats_v3 and :183-232 warp_img_feats_mgpu.
  * imgs_packed [V][hw][4] holds channels [c_off, c_off+c_cnt) of each source view;

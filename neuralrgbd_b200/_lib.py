@@ -21,6 +21,9 @@ SIGNATURES = {
     'nrgbd_plane_sweep_cost_packed': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_float, c_float, c_int,
                                               c_vp, c_vp, c_vp]),
+    'nrgbd_plane_sweep_dpv_packed': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_float, c_float, c_int,
+                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'nrgbd_warp_to_volume': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                      c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp]),
     'nrgbd_knet_input_volume': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,

@@ -926,13 +926,13 @@ static int forward_core(nrgbd_kvnet* e, bool steady, bool need_cur_refined, bool
   if (!e->rc) {
     {
     ProfScope ps(e, 1, ((1.0 + V) * (F + 3) + D + 3) * (double)hw * 4.0);
-    ENG_CALL(e, nrgbd_plane_sweep_cost_packed(feat.p + (size_t)V * featS, rgbq.p + (size_t)V * hw * 4, feat.p, rgbq.p, F, 3, V, D,
-                                              h, w, c0.K, Rs, ts, c0.rays, e->d_planes, c0.cx, c0.cy, e->sigma, e->metric,
-                                              e->ws_sweep, e->dpv_hwd /* scratch: cost */, st));
+    // fused D-Net head: plane-sweep cost + BV = log_softmax(-costV) (basic.py:299-300) + expected depth / confidence;
+    // the cost volume stays in registers (F >= 64, D <= 256), otherwise dpv_hwd serves as its scratch
+    const bool in_regs = F >= 64 && F <= 128 && D <= 256;
+    ENG_CALL(e, nrgbd_plane_sweep_dpv_packed(feat.p + (size_t)V * featS, rgbq.p + (size_t)V * hw * 4, feat.p, rgbq.p, F, 3, V, D,
+                                             h, w, c0.K, Rs, ts, c0.rays, e->d_planes, c0.cx, c0.cy, e->sigma, e->metric,
+                                             e->ws_sweep, in_regs ? nullptr : e->dpv_hwd, e->bv_cur_hwd, e->depth, e->conf, st));
     }
-    // BV = log_softmax(-costV) (basic.py:299-300)
-    ENG_CALL(e, nrgbd_dpv_normalize(e->dpv_hwd, 1, D, nullptr, 0, 0, -1.f, (int)hw, D, e->bv_cur_hwd, 1, D, e->d_planes,
-                                    e->depth, e->conf, st));
   }
   // ---- R-Net on the measurement (KVNET.py:134) ----------------------------------------------------
   const float* feat_ref = feat.p ? feat.p + (size_t)V * featS : nullptr;

@@ -19,6 +19,7 @@
 // plane with 4 coalesced LDG.128 per tap set; a transposing shuffle-reduction leaves
 // lane l with the total for plane d0+l. The narrow channels are handled plane-per-lane.
 #include "common.cuh"
+#include "../../include/nrgbd.h"
 
 namespace {
 
@@ -169,6 +170,190 @@ plane_sweep_kernel(const float4* __restrict__ ref_w, const float4* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second-generation kernel (C >= 64 wide channels, D <= 256): corner vectors are kept in REGISTERS across planes.
+//
+// Measured on the kernel above (profiles/r1_sweep_kernel_ncu_full.json): 158 M L1 sectors = 5.05 GB of L1 traffic for
+// 30.9 MB of algorithmic bytes - every (pixel, plane, view) re-fetched its four 268-byte corner vectors although, along
+// the epipolar line of one pixel, consecutive planes mostly hit the SAME corners (uniform depth planes: beyond the first
+// ~20 of 64 planes the total disparity change is about one texel) or the neighbouring column. Here the view loop is the
+// outer one and each lane keeps the four corner float4s of its channel slice from plane to plane: a plane whose (clamped)
+// corner offsets equal the previous plane's loads nothing, a one-texel step along x loads two corners instead of four.
+// The interpolation / distance / reduction arithmetic and its order are unchanged, so costs are bit-identical to the
+// kernel above. The per-plane totals stay in registers (lane l of the 16-lane group owns planes l, 16 + l, ...), and the
+// epilogue either stores the raw cost (est_swp_volume_v4 mirror) or finishes the D-Net head in place:
+// BV = log_softmax(-cost) (models/basic.py:299-300), expected depth sum exp(BV) d and confidence max exp(BV).
+// ---------------------------------------------------------------------------------------------------------------
+template <int PASSES, bool L1, int NB>      // NB = ceil(D / 16) plane batches (register-resident totals)
+__global__ void __launch_bounds__(256)
+plane_sweep2_kernel(const float4* __restrict__ ref_w, const float4* __restrict__ src_w, int G,
+                    const float4* __restrict__ ref_n, const float4* __restrict__ src_n,
+                    const float* __restrict__ t1, const float* __restrict__ KR,
+                    const float* __restrict__ rays, const float* __restrict__ dpl, int V, int D, int w,
+                    int h, float cx, float cy, float sigma, float* __restrict__ cost, float* __restrict__ bv,
+                    float* __restrict__ depth, float* __restrict__ conf) {
+  constexpr int LANES = 16;
+  constexpr int GROUPS_PER_BLOCK = 256 / LANES;
+  __shared__ TapRec recs[256];
+  // per-plane totals: thread t owns s_tot[b][t] (plane 16 b + lane of its pixel). Kept in shared memory so that the batch
+  // loop can stay ROLLED: fully unrolled over the NB batches the kernel was instruction-fetch bound (ncu: 2.5 "no
+  // instruction" stall cycles per issue with ~80 KB of code)
+  __shared__ float s_tot[NB][256];
+  const int hw = w * h;
+  const int lane = threadIdx.x % LANES;
+  const int grp = threadIdx.x / LANES;
+  int pix = blockIdx.x * GROUPS_PER_BLOCK + grp;
+  const bool live = pix < hw;
+  if (!live) pix = hw - 1;                       // keep the group converged; results discarded
+  const float Wf = (float)w, Hf = (float)h;
+  const float r0 = rays[pix], r1 = rays[hw + pix], r2 = rays[2 * hw + pix];
+  float4 refw[PASSES];
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    int g = lane + p * LANES;
+    refw[p] = (g < G) ? __ldg(ref_w + (size_t)pix * G + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 refn = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ref_n) refn = __ldg(ref_n + pix);
+  TapRec* myrecs = recs + grp * LANES;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) s_tot[b][threadIdx.x] = 0.f;
+
+  for (int v = 0; v < V; ++v) {
+    const float* kr = KR + v * 9;
+    const float t2x = dot3_chain(kr[0], kr[1], kr[2], r0, r1, r2);
+    const float t2y = dot3_chain(kr[3], kr[4], kr[5], r0, r1, r2);
+    const float t2z = dot3_chain(kr[6], kr[7], kr[8], r0, r1, r2);
+    const float t1x = t1[v * 3], t1y = t1[v * 3 + 1], t1z = t1[v * 3 + 2];
+    const float4* sw = src_w + (size_t)v * hw * G;
+    const float4* sn = src_n ? src_n + (size_t)v * hw : nullptr;
+    // corner vectors of the previous plane (this lane's channel slice of every pass) and their offsets
+    float4 ca[PASSES], cb[PASSES], cc[PASSES], ce[PASSES];
+    int4 po = make_int4(-1, -1, -1, -1);
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+      const int d0 = b * LANES;
+      if (d0 < D) {
+        const int dmine = min(d0 + lane, D - 1);
+        const float dval = __ldg(dpl + dmine);
+        float ix, iy;
+        plane_project(t1x, t1y, t1z, t2x, t2y, t2z, dval, cx, cy, Wf, Hf, ix, iy);
+        Tap2D tp = make_tap2d(ix, iy, w, h);
+        float wt[4] = {tp.w_nw, tp.w_ne, tp.w_sw, tp.w_se};
+        float dn = 0.f;                                     // narrow channels: this lane's own plane
+        if (sn) {
+          float4 a = __ldg(sn + tp.o_nw), bq = __ldg(sn + tp.o_ne), c = __ldg(sn + tp.o_sw), e = __ldg(sn + tp.o_se);
+          dn = dist4<L1>(bilerp4(a, bq, c, e, wt), refn, 0.f);
+        }
+        __syncwarp();
+        myrecs[lane].o[0] = tp.o_nw; myrecs[lane].o[1] = tp.o_ne; myrecs[lane].o[2] = tp.o_sw; myrecs[lane].o[3] = tp.o_se;
+        myrecs[lane].w[0] = wt[0]; myrecs[lane].w[1] = wt[1]; myrecs[lane].w[2] = wt[2]; myrecs[lane].w[3] = wt[3];
+        __syncwarp();
+        float part[LANES];
+#pragma unroll
+        for (int j = 0; j < LANES; ++j) {
+          const int4 o = *reinterpret_cast<const int4*>(myrecs[j].o);
+          const float4 wq = *reinterpret_cast<const float4*>(myrecs[j].w);
+          const float wj[4] = {wq.x, wq.y, wq.z, wq.w};
+          // group-uniform decisions (every lane reads the same record)
+          const bool same = o.x == po.x && o.y == po.y && o.z == po.z && o.w == po.w;
+          if (!same) {
+            const bool step_x = o.x == po.y && o.z == po.w;          // one texel to the right: west corners = old east corners
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+              const int g = lane + p * LANES;
+              if (g < G) {
+                if (step_x) { ca[p] = cb[p]; cc[p] = ce[p]; }
+                else { ca[p] = __ldg(sw + (size_t)o.x * G + g); cc[p] = __ldg(sw + (size_t)o.z * G + g); }
+                cb[p] = __ldg(sw + (size_t)o.y * G + g); ce[p] = __ldg(sw + (size_t)o.w * G + g);
+              }
+            }
+            po = o;
+          }
+          float acc = 0.f;
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p) {
+            const int g = lane + p * LANES;
+            if (g < G) acc = dist4<L1>(bilerp4(ca[p], cb[p], cc[p], ce[p], wj), refw[p], acc);
+          }
+          part[j] = acc;
+        }
+        // transposing reduction: afterwards lane l holds the sum over lanes of part[l]
+#pragma unroll
+        for (int s = LANES / 2; s >= 1; s >>= 1) {
+          const bool upper = (lane & s) != 0;
+#pragma unroll
+          for (int j = 0; j < s; ++j) {
+            float keep = upper ? part[j + s] : part[j];
+            float send = upper ? part[j] : part[j + s];
+            part[j] = keep + __shfl_xor_sync(0xffffffffu, send, s, 32);
+          }
+        }
+        const float dist = dn + part[0];
+        s_tot[b][threadIdx.x] = __fadd_rn(s_tot[b][threadIdx.x], __fdiv_rn(dist, sigma));   // costV += dist / sigma  (homography.py:325)
+      }
+    }
+  }
+  // ---- epilogue ----
+  float tot[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) tot[b] = s_tot[b][threadIdx.x];
+  if (cost) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int d = b * LANES + lane;
+      if (live && d < D) cost[(size_t)pix * D + d] = tot[b];
+    }
+  }
+  if (bv || depth || conf) {
+    // BV = log_softmax(-cost) over the D planes of this pixel: max / sum over the 16-lane group
+    float m = -INFINITY;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) if (b * LANES + lane < D) m = fmaxf(m, -tot[b]);
+#pragma unroll
+    for (int s = LANES / 2; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s, 32));
+    float se = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) if (b * LANES + lane < D) se += expf(-tot[b] - m);
+#pragma unroll
+    for (int s = LANES / 2; s >= 1; s >>= 1) se += __shfl_xor_sync(0xffffffffu, se, s, 32);
+    const float ls = logf(se);
+    float dep = 0.f, cf = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int d = b * LANES + lane;
+      if (d < D) {
+        const float o = (-tot[b] - m) - ls;
+        if (bv && live) bv[(size_t)pix * D + d] = o;
+        const float pr = expf(o);
+        dep += pr * __ldg(dpl + d); cf = fmaxf(cf, pr);
+      }
+    }
+#pragma unroll
+    for (int s = LANES / 2; s >= 1; s >>= 1) { dep += __shfl_xor_sync(0xffffffffu, dep, s, 32); cf = fmaxf(cf, __shfl_xor_sync(0xffffffffu, cf, s, 32)); }
+    if (live && lane == 0) { if (depth) depth[pix] = dep; if (conf) conf[pix] = cf; }
+  }
+}
+
+template <bool L1>
+int launch_sweep2(int passes, int D, dim3 grid, cudaStream_t st, const float4* ref_w, const float4* src_w, int G, const float4* ref_n,
+                  const float4* src_n, const float* t1, const float* KR, const float* rays, const float* dpl, int V, int w, int h, float cx,
+                  float cy, float sigma, float* cost, float* bv, float* depth, float* conf) {
+  const int nb = (D + 15) / 16;
+#define NRGBD_SWEEP2(P, NBV)                                                                                                     \
+  plane_sweep2_kernel<P, L1, NBV><<<grid, 256, 0, st>>>(ref_w, src_w, G, ref_n, src_n, t1, KR, rays, dpl, V, D, w, h, cx, cy, sigma, \
+                                                        cost, bv, depth, conf)
+  if (passes == 1) {
+    if (nb <= 2) NRGBD_SWEEP2(1, 2); else if (nb <= 4) NRGBD_SWEEP2(1, 4); else if (nb <= 8) NRGBD_SWEEP2(1, 8); else NRGBD_SWEEP2(1, 16);
+  } else if (passes == 2) {
+    if (nb <= 2) NRGBD_SWEEP2(2, 2); else if (nb <= 4) NRGBD_SWEEP2(2, 4); else if (nb <= 8) NRGBD_SWEEP2(2, 8); else NRGBD_SWEEP2(2, 16);
+  } else {
+    return NRGBD_ERR_UNSUPPORTED;
+  }
+#undef NRGBD_SWEEP2
+  return NRGBD_OK;
+}
+
 // [C][hw] (NCHW plane-major) -> wide [hw][Cw] (+ zero pad) and narrow [hw][4]
 __global__ void pack_features_kernel(const float* __restrict__ in, int C, int hw, int Cw_src, int Cw,
                                      float* __restrict__ wide, float* __restrict__ narrow) {
@@ -270,17 +455,14 @@ int nrgbd_transpose2d(const float* in, int A, int B, float* out, cudaStream_t st
   return NRGBD_OK;
 }
 
-// Cost volume from packed (channel-last) features. cost is [h*w][D].
-// ws: V*12 floats of device scratch (term1, K.R).
-int nrgbd_plane_sweep_cost_packed(const float* ref_wide, const float* ref_narrow, const float* src_wide,
-                                  const float* src_narrow, int Cw, int Cn, int V, int D, int h, int w,
-                                  const float* K, const float* R, const float* t, const float* rays,
-                                  const float* d_planes, float cx, float cy, float sigma, int metric,
-                                  float* ws, float* cost_hwd, cudaStream_t st) {
+static int sweep_impl(const float* ref_wide, const float* ref_narrow, const float* src_wide, const float* src_narrow, int Cw, int Cn,
+                      int V, int D, int h, int w, const float* K, const float* R, const float* t, const float* rays,
+                      const float* d_planes, float cx, float cy, float sigma, int metric, float* ws, float* cost_hwd, float* bv_hwd,
+                      float* depth, float* conf, cudaStream_t st) {
   NRGBD_REQUIRE(V > 0 && D > 0 && h > 0 && w > 0, "empty problem");
   NRGBD_REQUIRE(Cw % 4 == 0 && Cn >= 0 && Cn <= 4 && Cw + Cn > 0, "bad channel split");
   NRGBD_REQUIRE((Cw == 0 || (ref_wide && src_wide)) && (Cn == 0 || (ref_narrow && src_narrow)), "null features");
-  NRGBD_REQUIRE(K && R && t && rays && d_planes && ws && cost_hwd, "null pointer");
+  NRGBD_REQUIRE(K && R && t && rays && d_planes && ws && (cost_hwd || bv_hwd || depth || conf), "null pointer");
   if (metric != 0 && metric != 1) {
     nrgbd_set_error("undefined metric for feature distance ...");   // homography.py:329
     return NRGBD_ERR_BAD_ARG;
@@ -289,18 +471,30 @@ int nrgbd_plane_sweep_cost_packed(const float* ref_wide, const float* ref_narrow
   float* KR = ws + 3 * V;
   sweep_setup_kernel<<<ceil_div(V, 32), 32, 0, st>>>(K, R, t, V, t1, KR);
   const int G = Cw / 4;
+  const int hw = h * w;
+  const float4* rw = reinterpret_cast<const float4*>(ref_wide);
+  const float4* sw = reinterpret_cast<const float4*>(src_wide);
+  const float4* rn = Cn ? reinterpret_cast<const float4*>(ref_narrow) : nullptr;
+  const float4* sn = Cn ? reinterpret_cast<const float4*>(src_narrow) : nullptr;
+  const bool fused_head = bv_hwd || depth || conf;
+  if (G >= 16 && G <= 32 && D <= 256) {
+    // register-cached corners (plane_sweep2_kernel), optional fused D-Net head
+    dim3 grid(ceil_div((long long)hw * 16, 256));
+    const int passes = ceil_div(G, 16);
+    int rc = metric == 0 ? launch_sweep2<false>(passes, D, grid, st, rw, sw, G, rn, sn, t1, KR, rays, d_planes, V, w, h, cx, cy, sigma, cost_hwd,
+                                                bv_hwd, depth, conf)
+                         : launch_sweep2<true>(passes, D, grid, st, rw, sw, G, rn, sn, t1, KR, rays, d_planes, V, w, h, cx, cy, sigma, cost_hwd,
+                                               bv_hwd, depth, conf);
+    if (rc == NRGBD_OK) { NRGBD_COUNT(2); NRGBD_LAUNCH_CHECK(); return NRGBD_OK; }
+  }
+  NRGBD_REQUIRE(cost_hwd || !fused_head, "this channel configuration needs a cost buffer (the fused head runs as a second pass)");
   // lane-group width: the widest power of two (<=16) that keeps every lane busy in pass 0
   int lanes = 1;
   if (G >= 16) lanes = 16; else if (G >= 4) lanes = 4;
   int passes = G == 0 ? 0 : ceil_div(G, lanes);
   if (passes == 3) passes = 4;
   if (passes > 4) { nrgbd_set_error("plane sweep supports at most 256 wide channels per call"); return NRGBD_ERR_UNSUPPORTED; }
-  const int hw = h * w;
   dim3 grid(ceil_div((long long)hw * lanes, 256));
-  const float4* rw = reinterpret_cast<const float4*>(ref_wide);
-  const float4* sw = reinterpret_cast<const float4*>(src_wide);
-  const float4* rn = Cn ? reinterpret_cast<const float4*>(ref_narrow) : nullptr;
-  const float4* sn = Cn ? reinterpret_cast<const float4*>(src_narrow) : nullptr;
   int rc;
 #define NRGBD_SWEEP_LANES(L)                                                                               \
   rc = metric == 0 ? launch_sweep_p<L, false>(passes, grid, st, rw, sw, G, rn, sn, t1, KR, rays, d_planes, V, \
@@ -312,7 +506,32 @@ int nrgbd_plane_sweep_cost_packed(const float* ref_wide, const float* ref_narrow
   if (rc != NRGBD_OK) { nrgbd_set_error("plane sweep: unsupported channel configuration"); return rc; }
   NRGBD_COUNT(2);
   NRGBD_LAUNCH_CHECK();
+  if (fused_head) return nrgbd_dpv_normalize(cost_hwd, 1, D, nullptr, 0, 0, -1.f, hw, D, bv_hwd, 1, D, d_planes, depth, conf, (nrgbd_stream_t)st);
   return NRGBD_OK;
+}
+
+// Cost volume from packed (channel-last) features. cost is [h*w][D].
+// ws: V*12 floats of device scratch (term1, K.R).
+int nrgbd_plane_sweep_cost_packed(const float* ref_wide, const float* ref_narrow, const float* src_wide,
+                                  const float* src_narrow, int Cw, int Cn, int V, int D, int h, int w,
+                                  const float* K, const float* R, const float* t, const float* rays,
+                                  const float* d_planes, float cx, float cy, float sigma, int metric,
+                                  float* ws, float* cost_hwd, cudaStream_t st) {
+  NRGBD_REQUIRE(cost_hwd, "null pointer");
+  return sweep_impl(ref_wide, ref_narrow, src_wide, src_narrow, Cw, Cn, V, D, h, w, K, R, t, rays, d_planes, cx, cy, sigma, metric, ws,
+                    cost_hwd, nullptr, nullptr, nullptr, st);
+}
+
+// The whole D-Net head after the feature CNN in one kernel (models/basic.py:270-300): plane-sweep cost, then
+// BV = log_softmax(-cost) [h*w][D] (pixel-major), expected depth sum exp(BV) d and confidence max exp(BV) (any of the three
+// may be NULL); the cost volume itself is written only when cost_hwd is given.
+int nrgbd_plane_sweep_dpv_packed(const float* ref_wide, const float* ref_narrow, const float* src_wide,
+                                 const float* src_narrow, int Cw, int Cn, int V, int D, int h, int w,
+                                 const float* K, const float* R, const float* t, const float* rays,
+                                 const float* d_planes, float cx, float cy, float sigma, int metric,
+                                 float* ws, float* cost_hwd, float* bv_hwd, float* depth, float* conf, cudaStream_t st) {
+  return sweep_impl(ref_wide, ref_narrow, src_wide, src_narrow, Cw, Cn, V, D, h, w, K, R, t, rays, d_planes, cx, cy, sigma, metric, ws,
+                    cost_hwd, bv_hwd, depth, conf, st);
 }
 
 }  // extern "C"
