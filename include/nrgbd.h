@@ -92,6 +92,14 @@ int nrgbd_knet_input_volume(const float* src_rgb_packed, const float* ref_rgb_pa
                             const float* d_planes, float cx, float cy, float* ws, float* out,
                             nrgbd_stream_t stream);
 
+/* the same volume, optionally (also / only: out may be NULL) as the split-fp16 operand pair (out_hi, out_lo: half
+ * [D][hw][CK], CK = 16 or 32) of the f16-pair convolution that consumes it - see nrgbd_conv_nhwc_h2 */
+int nrgbd_knet_input_volume_pair(const float* src_rgb_packed, const float* ref_rgb_packed,
+                                 const float* bv_cur_hwd, const float* bv_pred_hwd, int V, int D, int h, int w,
+                                 int CK, const float* K, const float* R, const float* t, const float* rays,
+                                 const float* d_planes, float cx, float cy, float* ws, float* out, void* out_hi,
+                                 void* out_lo, nrgbd_stream_t stream);
+
 /* ---- a12: DPV re-projection -----------------------------------------------------------------
  * replaces warping/homography.py:654-723 resample_vol_cuda + :873-887 _set_vol_border (+ the
  * clamp of test_utils/test_KVNet.py:54-59 when do_clamp != 0). Element (d,pix) of vol/out lives at
@@ -136,6 +144,19 @@ int nrgbd_plane_sweep_backward_packed(const float* ref_wide, const float* ref_na
 /* Inverse of nrgbd_pack_features: n_img images of wide [hw][C - C%4] (+ narrow [hw][4]) -> NCHW [C][hw]. */
 int nrgbd_unpack_features(const float* wide, const float* narrow, int C, int hw, int n_img, float* nchw,
                           nrgbd_stream_t stream);
+
+/* ---- f-3: depth-map back-warp of the local bundle adjustment and its gradients -------------------------------------
+ * replaces warping/homography.py:479-529 back_warp_th_Rt_msrc and :530-574 back_warp_th_Rt (consumer:
+ * ICP/opt_pose_numerical.py:99-160, which differentiates the warped image w.r.t. R and t through F.grid_sample's grid).
+ * imgs [N][C][H][W], dmap [H][W] (reference depth), Rs [N][3][3], ts [N][3] (reference -> source), K 3x3
+ * (cam_intrinsic['intrinsic_M_cuda']), rays [3][H*W] (cam_intrinsic['unit_ray_array_2D']) -> out [N][C][H][W]. */
+int nrgbd_lba_back_warp(const float* imgs, const float* dmap, const float* Rs, const float* ts, const float* K,
+                        const float* rays, int N, int C, int H, int W, float* out, nrgbd_stream_t stream);
+/* grad_out [N][C][H][W] -> g_R [N][3][3] and g_t [N][3] (both or neither), g_imgs [N][C][H][W] (optional; scatter-added
+ * with atomics, like ATen's grid_sampler backward). ws: N * 12 doubles of device scratch. */
+int nrgbd_lba_back_warp_backward(const float* grad_out, const float* imgs, const float* dmap, const float* Rs,
+                                 const float* ts, const float* K, const float* rays, int N, int C, int H, int W,
+                                 float* g_imgs, float* g_R, float* g_t, double* ws, nrgbd_stream_t stream);
 
 /* ---- f-4: input stage (replaces mdataloader/scanNet.py:368-369 PIL nearest resize and
  * mdataloader/m_preprocess.py:15-21 ToTensor + Normalize, both host-side per frame) ------------------------------

@@ -948,9 +948,26 @@ static int forward_core(nrgbd_kvnet* e, bool steady, bool need_cur_refined, bool
     // ---- K-Net (KVNET.py:147-173) ------------------------------------------------------------------
     const Camera& c1 = e->cam[1];
     const int CK = 3 * V + 4;
-    Act vol = acquire(e, 1, D, h, w, CK);
-    ENG_CALL(e, nrgbd_knet_input_volume(rgbq.p, rgbq.p + (size_t)V * hw * 4, e->bv_cur_hwd, e->prior_hwd, V, D, h, w, vol.Cs,
-                                        c1.K, Rs, ts, c1.rays, e->d_planes, c1.cx, c1.cy, e->ws_sweep, vol.p, st));
+    Act vol;
+    if (e->conv_math == 2 && pad32(CK) == 32) {
+      // f16-pair mode: the volume is written directly as the operand pair of dres0.0 (no fp32 volume, no split pass);
+      // vol.p is only the key of the pair buffers (a 16-byte block)
+      vol.N = 1; vol.D = D; vol.H = h; vol.W = w; vol.C = CK; vol.Cs = 32;
+      vol.p = e->pool.acquire(16);
+      PairBuf pb;
+      pb.hi = e->pool.acquire((size_t)vol.floats() * 2);
+      pb.lo = e->pool.acquire((size_t)vol.floats() * 2);
+      if (!vol.p || !pb.hi || !pb.lo) { if (!e->rc) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; } }
+      else {
+        ENG_CALL(e, nrgbd_knet_input_volume_pair(rgbq.p, rgbq.p + (size_t)V * hw * 4, e->bv_cur_hwd, e->prior_hwd, V, D, h, w, vol.Cs,
+                                                 c1.K, Rs, ts, c1.rays, e->d_planes, c1.cx, c1.cy, e->ws_sweep, nullptr, pb.hi, pb.lo, st));
+        e->pairs[vol.p] = pb;
+      }
+    } else {
+      vol = acquire(e, 1, D, h, w, CK);
+      ENG_CALL(e, nrgbd_knet_input_volume(rgbq.p, rgbq.p + (size_t)V * hw * 4, e->bv_cur_hwd, e->prior_hwd, V, D, h, w, vol.Cs,
+                                          c1.K, Rs, ts, c1.rays, e->d_planes, c1.cx, c1.cy, e->ws_sweep, vol.p, st));
+    }
     Act gain = kv_net(e, vol);
     release(e, vol);
     // DPV = log_softmax(gain + BV_predict) (:172-173); gain is [D][hw], prior pixel-major

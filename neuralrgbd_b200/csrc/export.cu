@@ -21,38 +21,59 @@ __device__ __forceinline__ unsigned short to_u16(float x) {
   return (unsigned short)(int)x;
 }
 
+// Four consecutive pixels per thread (one 16-byte load per plane, eight planes in flight: 128 bytes per thread outstanding,
+// ~64 KB per SM); the per-pixel sums stay sequential over the planes, as in the reference's loop. VEC = 1 handles a ragged tail /
+// unaligned volumes.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 export_depth_conf_kernel(const float* __restrict__ bv, const float* __restrict__ d_candi, int D, long long HW,
                          float depth_scale, float conf_scale, float* __restrict__ dmap, float* __restrict__ conf,
-                         unsigned short* __restrict__ dmap_u16, unsigned short* __restrict__ conf_u16) {
+                         unsigned short* __restrict__ dmap_u16, unsigned short* __restrict__ conf_u16, long long p_begin) {
   extern __shared__ float dc[];
   for (int i = threadIdx.x; i < D; i += blockDim.x) dc[i] = d_candi[i];
   __syncthreads();
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
+  const long long p = p_begin + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (p + VEC > HW) return;
   // products are rounded before they are added (exp(BV) * Depth_val_vol is materialised in the reference)
-  float acc = 0.f, m = -INFINITY;
+  float acc[VEC], m[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { acc[k] = 0.f; m[k] = -INFINITY; }
   int d = 0;
   for (; d + 8 <= D; d += 8) {                 // eight independent loads in flight per thread (HBM latency)
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldg(bv + (long long)(d + j) * HW + p);
+    float v[8][VEC];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      acc = __fadd_rn(acc, __fmul_rn(expf(v[j]), dc[d + j]));
-      m = fmaxf(m, v[j]);
+      if (VEC == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(bv + (long long)(d + j) * HW + p));
+        v[j][0] = q.x; v[j][1 % VEC] = q.y; v[j][2 % VEC] = q.z; v[j][3 % VEC] = q.w;
+      } else {
+        v[j][0] = __ldg(bv + (long long)(d + j) * HW + p);
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        acc[k] = __fadd_rn(acc[k], __fmul_rn(expf(v[j][k]), dc[d + j]));
+        m[k] = fmaxf(m[k], v[j][k]);
+      }
   }
   for (; d < D; ++d) {
-    const float v = __ldg(bv + (long long)d * HW + p);
-    acc = __fadd_rn(acc, __fmul_rn(expf(v), dc[d]));
-    m = fmaxf(m, v);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float v = __ldg(bv + (long long)d * HW + p + k);
+      acc[k] = __fadd_rn(acc[k], __fmul_rn(expf(v), dc[d]));
+      m[k] = fmaxf(m[k], v);
+    }
   }
-  const float c = expf(m);
-  if (dmap) dmap[p] = acc;
-  if (conf) conf[p] = c;
-  if (dmap_u16) dmap_u16[p] = to_u16(__fmul_rn(acc, depth_scale));
-  if (conf_u16) conf_u16[p] = to_u16(__fmul_rn(c, conf_scale));
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float c = expf(m[k]);
+    if (dmap) dmap[p + k] = acc[k];
+    if (conf) conf[p + k] = c;
+    if (dmap_u16) dmap_u16[p + k] = to_u16(__fmul_rn(acc[k], depth_scale));
+    if (conf_u16) conf_u16[p + k] = to_u16(__fmul_rn(c, conf_scale));
+  }
 }
 
 }  // namespace
@@ -63,10 +84,23 @@ extern "C" int nrgbd_export_depth_conf(const float* log_dpv, const float* d_cand
   NRGBD_REQUIRE(log_dpv && d_candi, "null pointer");
   NRGBD_REQUIRE(D >= 1 && D <= 4096 && HW >= 1, "bad volume extent");
   NRGBD_REQUIRE(dmap || conf || dmap_u16 || conf_u16, "no output requested");
-  const long long blocks = (HW + 255) / 256;
-  export_depth_conf_kernel<<<(unsigned)blocks, 256, D * sizeof(float), (cudaStream_t)st>>>(log_dpv, d_candi, D, HW, depth_scale, conf_scale,
-                                                                                        dmap, conf, dmap_u16, conf_u16);
-  NRGBD_COUNT(1);
+  // vector body (4 pixels per thread) when the planes are 16-byte aligned, scalar kernel for the tail / unaligned volumes
+  long long body = 0;
+  if (HW % 4 == 0 && ((uintptr_t)log_dpv & 15) == 0) body = HW;
+  int launches = 0;
+  if (body > 0) {
+    const long long blocks = (body / 4 + 255) / 256;
+    export_depth_conf_kernel<4><<<(unsigned)blocks, 256, D * sizeof(float), (cudaStream_t)st>>>(log_dpv, d_candi, D, HW, depth_scale, conf_scale,
+                                                                                             dmap, conf, dmap_u16, conf_u16, 0);
+    ++launches;
+  }
+  if (body < HW) {
+    const long long blocks = (HW - body + 255) / 256;
+    export_depth_conf_kernel<1><<<(unsigned)blocks, 256, D * sizeof(float), (cudaStream_t)st>>>(log_dpv, d_candi, D, HW, depth_scale, conf_scale,
+                                                                                             dmap, conf, dmap_u16, conf_u16, body);
+    ++launches;
+  }
+  NRGBD_COUNT(launches);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;
 }

@@ -285,3 +285,69 @@ def resample_vol_cuda(src_vol, rel_extM, cam_intrinsic=None, d_candi=None, d_can
                                    _F(z_half), _F(z_radius), _F(float(padding_value)), 1 if clamp is not None else 0,
                                    _F(lo), _F(hi), ptr(out), H * W, 1, _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f-3: depth-map back-warp of the local bundle adjustment (warping/homography.py:479-574) with the gradients
+# ICP/opt_pose_numerical.py:99-160 takes through it (w.r.t. R, t; also w.r.t. the images, as autograd would give)
+# ---------------------------------------------------------------------------------------------------------------
+class _LbaBackWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, imgs, dmap, Rs, ts, K, rays):
+        L = _lib.lib()
+        N, C, H, W = imgs.shape
+        out = torch.empty((N, C, H, W), device=imgs.device, dtype=torch.float32)
+        check(L.nrgbd_lba_back_warp(ptr(imgs), ptr(dmap), ptr(Rs), ptr(ts), ptr(K), ptr(rays), N, C, H, W, ptr(out), _stream()))
+        ctx.save_for_backward(imgs, dmap, Rs, ts, K, rays)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        imgs, dmap, Rs, ts, K, rays = ctx.saved_tensors
+        L = _lib.lib()
+        N, C, H, W = imgs.shape
+        need_img, need_pose = ctx.needs_input_grad[0], ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError('back_warp_th_Rt: no gradient with respect to the depth map (the reference optimises R, t only)')
+        g_img = torch.empty_like(imgs) if need_img else None
+        g_R = torch.empty((N, 3, 3), device=imgs.device, dtype=torch.float32) if need_pose else None
+        g_t = torch.empty((N, 3), device=imgs.device, dtype=torch.float32) if need_pose else None
+        if need_img or need_pose:
+            ws = torch.empty(N * 12, device=imgs.device, dtype=torch.float64)
+            go = grad_out.float().contiguous()
+            with torch.cuda.device(imgs.device):
+                check(L.nrgbd_lba_back_warp_backward(ptr(go), ptr(imgs), ptr(dmap), ptr(Rs), ptr(ts), ptr(K), ptr(rays), N, C, H, W,
+                                                     ptr(g_img), ptr(g_R), ptr(g_t), ctypes.c_void_p(ws.data_ptr()), _stream()))
+        return g_img, None, g_R if ctx.needs_input_grad[2] else None, g_t if ctx.needs_input_grad[3] else None, None, None
+
+
+def back_warp_th_Rt_msrc(imgs_src, dmap, Rs, ts, cam_intrinsic):
+    '''
+    imgs_src - NCHW multiple src frames
+    Rs, ts - Rs[iview, ... ], ts[iview, ...] rotation/translation from ref to src view
+    Given the depth map ( 2D torch tensor), the camera poses (R,t, as torch.tensor) warp the src. image
+    (warping/homography.py:479-529; one fused kernel, differentiable w.r.t. imgs_src, Rs and ts)
+    '''
+    assert isinstance(imgs_src, torch.Tensor)
+    dev = _dev(imgs_src)
+    npts = dmap.numel()
+    assert cam_intrinsic['unit_ray_array_2D'].shape[1] == npts
+    K, rays = _cam_tensors(cam_intrinsic, dev)
+    with torch.cuda.device(dev):
+        imgs = imgs_src.float().contiguous()
+        d = dmap.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        Rs_ = Rs.to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
+        ts_ = ts.to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
+        assert Rs_.shape[0] == imgs.shape[0] and ts_.shape[0] == imgs.shape[0]
+        return _LbaBackWarp.apply(imgs, d, Rs_, ts_, K, rays)
+
+
+def back_warp_th_Rt(img_src, dmap, R, t, cam_intrinsic):
+    '''
+    img_src - NCHW
+    Given the depth map ( 2D torch tensor), the camera poses (R,t, as torch.tensor) warp the src. image
+    R, t - rotation/translation from ref to src view   (warping/homography.py:530-574)
+    '''
+    assert isinstance(R, torch.Tensor) and isinstance(t, torch.Tensor), 'R,t should be torch tensors'
+    assert img_src.shape[0] == 1
+    return back_warp_th_Rt_msrc(img_src, dmap, R.reshape(1, 3, 3), t.reshape(1, 3), cam_intrinsic)

@@ -107,6 +107,40 @@ def main():
         check(L.nrgbd_export_depth_conf(ptr(bvf), ptr(dpl), D, HW, F(1000.), F(1000.), ptr(dm), ptr(cf), ptr(d16), ptr(c16), st()))
     med, mn = timeit(export)
     res['export_depth_conf'] = dict(us_med=med, us_min=mn, alg_MB=(D * HW * 4 + 12 * HW) / 1e6, GBps=(D * HW * 4 + 12 * HW) / med / 1e3)
+    # K-Net input volume rows (fp32 and operand-pair outputs), LBA back-warp (f-3) forward / backward at full resolution
+    refq = torch.randn(hw, 4, device=dev); prior = torch.log_softmax(torch.randn(hw, D, device=dev), 1).contiguous()
+    volf = torch.empty(D, hw, 32, device=dev); vh = torch.empty(D, hw, 32, device=dev, dtype=torch.float16); vl = torch.empty_like(vh)
+
+    def knet_f32():
+        check(L.nrgbd_knet_input_volume(ptr(rgb), ptr(refq), ptr(bv), ptr(prior), V, D, h, w, 32, ptr(K), ptr(R), ptr(t), ptr(rays), ptr(dpl),
+                                        F(w / 2), F(h / 2), ptr(ws), ptr(volf), st()))
+
+    def knet_pair():
+        check(L.nrgbd_knet_input_volume_pair(ptr(rgb), ptr(refq), ptr(bv), ptr(prior), V, D, h, w, 32, ptr(K), ptr(R), ptr(t), ptr(rays), ptr(dpl),
+                                             F(w / 2), F(h / 2), ptr(ws), None, ptr(vh), ptr(vl), st()))
+    med, mn = timeit(knet_f32)
+    res['knet_input_volume_f32'] = dict(us_med=med, us_min=mn, GBps=(D * hw * 32 * 4 + 2 * D * hw * 4) / med / 1e3)
+    med, mn = timeit(knet_pair)
+    res['knet_input_volume_pair'] = dict(us_med=med, us_min=mn, GBps=(D * hw * 32 * 4 + 2 * D * hw * 4) / med / 1e3)
+    Hf, Wf = 4 * h, 4 * w
+    imgs = torch.randn(V, 3, Hf, Wf, device=dev); dm_full = (0.8 + 2.5 * torch.rand(Hf, Wf, device=dev))
+    xsf = (np.arange(Wf) + .5) / Wf * 2 - 1; ysf = (np.arange(Hf) + .5) / Hf * 2 - 1
+    raysf = np.stack([np.tile(320 / 585. * xsf[None], (Hf, 1)), np.tile(240 / 585. * ysf[:, None], (1, Wf)), np.ones((Hf, Wf))]).reshape(3, -1)
+    raysf = torch.from_numpy(raysf.astype(np.float32)).to(dev)
+    Kf = torch.tensor([[4 * fx, 0, Wf / 2], [0, 4 * fy, Hf / 2], [0, 0, 1]], dtype=torch.float32, device=dev)
+    wout = torch.empty_like(imgs); gout = torch.randn_like(imgs); gimg = torch.empty_like(imgs)
+    gR = torch.empty(V, 3, 3, device=dev); gt = torch.empty(V, 3, device=dev); wsd = torch.empty(V * 12, device=dev, dtype=torch.float64)
+
+    def lba_f():
+        check(L.nrgbd_lba_back_warp(ptr(imgs), ptr(dm_full), ptr(R), ptr(t), ptr(Kf), ptr(raysf), V, 3, Hf, Wf, ptr(wout), st()))
+
+    def lba_b():
+        check(L.nrgbd_lba_back_warp_backward(ptr(gout), ptr(imgs), ptr(dm_full), ptr(R), ptr(t), ptr(Kf), ptr(raysf), V, 3, Hf, Wf, None, ptr(gR), ptr(gt),
+                                             ctypes.c_void_p(wsd.data_ptr()), st()))
+    med, mn = timeit(lba_f)
+    res['lba_back_warp_4views_640x480'] = dict(us_med=med, us_min=mn, GBps=(2 * V * 3 * Hf * Wf * 4 + 4 * Hf * Wf * 4) / med / 1e3)
+    med, mn = timeit(lba_b)
+    res['lba_back_warp_pose_gradients'] = dict(us_med=med, us_min=mn, GBps=(2 * V * 3 * Hf * Wf * 4 + 4 * Hf * Wf * 4) / med / 1e3)
     print(json.dumps(dict(shape=dict(h=h, w=w, C=C, V=V, D=D), kernels=res), indent=1))
 
 
