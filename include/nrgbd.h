@@ -211,10 +211,13 @@ int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, cons
                          float eps, float* run_mean, float* run_var, float momentum, const float* res, int relu,
                          long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);
 /* same pass, also (or only: y may be NULL) emitting the result as the split-fp16 operand pair (y_hi, y_lo: half tensors with
- * x's layout) of the f16-pair convolution that consumes it - see nrgbd_conv_nhwc_h2 */
-int nrgbd_bn_apply_stats_pair(const float* x, const double* stats, double count, const float* gamma, const float* beta,
+ * x's layout; both may be NULL) of the f16-pair convolution that consumes it - see nrgbd_conv_nhwc_h2. rezero_counter
+ * (optional, a zero-initialised device word): the last block to have read `stats` sets them back to zero, so the next
+ * convolution accumulates into a clean buffer without a memset in between. */
+int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const float* gamma, const float* beta,
                               float eps, float* run_mean, float* run_var, float momentum, const float* res, int relu,
-                              long long n_pos, int Cs, int C, float* y, void* y_hi, void* y_lo, nrgbd_stream_t stream);
+                              long long n_pos, int Cs, int C, float* y, void* y_hi, void* y_lo,
+                              unsigned int* rezero_counter, nrgbd_stream_t stream);
 /* y = [relu](x*scale + shift) [+ res] over n_pos positions of Cs channels (C logical). */
 int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const float* res, int relu,
                    long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);

@@ -364,23 +364,28 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
     if (dbg && lane == 0) { dbg[3] = clock64(); dbg[11] = w_a; dbg[12] = w_b; dbg[13] = w_t; dbg[14] = t_loop; }
   } else {
-    // ===== epilogue (two groups of four warps; group g owns the 32-channel slabs g, g + 2, ...) =====
+    // ===== epilogue: two independent groups of four warps. The work of an item is cut into units = (sub-tile, 32-channel
+    // slab); group g takes units g, g + 2, ... through its OWN 16 KB staging slab (TMA store + BatchNorm column sums), so
+    // the groups never wait for each other and a 32-channel layer (one slab per sub-tile) still keeps both busy =====
     const int cg = warp >= 6 ? 1 : 0;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                  // GEMM row = TMEM lane = pixel within the tile
     const int py0 = r / TW, px = r % TW;
-    uint8_t* ep = smem_gen + stage_off;
+    uint8_t* ep = smem_gen + stage_off + cg * 16384;
+    const uint32_t ep_addr = smem_base + stage_off + (uint32_t)(cg * 16384);
     const bool tma_out = p.tma_store != 0 && !(p.dev_flags & 32);
     const bool want_stats = p.stats && !(p.dev_flags & 16);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool storer = tma_out && q == 0 && lane == 0;            // one thread per group
     int acc = 0; uint32_t acc_ph = 0;
     long long w_t = 0, t_ep = 0;
-    // BatchNorm sums: every epilogue thread owns one (column, row-segment) pair and accumulates it in registers over all
-    // items of this CTA's current Cout chunk; one pair of global atomics per thread per chunk instead of per tile (with the
-    // per-tile form the 32-channel layers spent most of their time queueing on 64 hot L2 addresses)
-    double st1 = 0.0, st2 = 0.0;
-    int st_col = -1;
+    // BatchNorm sums: every thread owns one (column, 32-row segment) of its group's slab and accumulates it in registers over
+    // all the units it sees (two register sets: a group alternates between at most two slabs); global atomics only when the
+    // column changes and at the end - per-tile atomics had the 32-channel layers queueing on 64 hot L2 addresses
+    double sa1 = 0.0, sa2 = 0.0, sb1 = 0.0, sb2 = 0.0;
+    int sa_col = -1, sb_col = -1;
+    const int e_g = q * 32 + lane;
+    const int s_col = e_g & 31, s_seg = e_g >> 5;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int chunk = item / tiles;
       int t = item - chunk * tiles;
@@ -393,119 +398,125 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int n_here = min(BN, p.Cout - cbase);   // logical channels of this item
       const int rows_left = p.Hy - oy00;
       const int nsub = rows_left >= TH * p.msub ? p.msub : (rows_left + TH - 1) / TH;
+      const int n_slabs = (BN + 31) >> 5;
+      const int n_units = nsub * n_slabs;
       const bool vec_ok = ((p.Cs_out | (p.c_off + cbase)) & 3) == 0;
-      long long te0 = 0;
-     for (int sub = 0; sub < nsub; ++sub) {
-      const int oy0 = oy00 + sub * TH;
-      const int iy = oy0 + py0, ix = ox0 + px;
-      const bool valid = iy < p.Hy && ix < p.Wx;
-      const int oy = iy * p.out_stride + p.out_off_y, ox = ix * p.out_stride + p.out_off_x;
-      float* dst = p.y + ((((long long)n0 * p.Dout + z0) * p.Hout + oy) * p.Wout + ox) * (long long)p.Cs_out + p.c_off + cbase;
-      // the staging slabs are free again once the previous sub-tile's TMA stores have read them and its column sums are done
-      if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 3, %0;" ::"n"(128 * EP_GROUPS) : "memory");
-      if (sub == 0) {
-        mbar_wait_t(bar_tfull + 8 * acc, acc_ph, timed && threadIdx.x == 64, w_t);
-        te0 = (timed && threadIdx.x == 64) ? clock64() : 0;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      const uint32_t acc_base = lane_base + (uint32_t)(acc * p.acc_stride + sub * 2 * BN);
-      for (int c0 = cg * 32; c0 < BN; c0 += ((c0 & 16) ? 32 * EP_GROUPS - 16 : 16)) {
-        uint32_t vm[16], vc[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(vm[0]), "=r"(vm[1]), "=r"(vm[2]), "=r"(vm[3]), "=r"(vm[4]), "=r"(vm[5]), "=r"(vm[6]), "=r"(vm[7]), "=r"(vm[8]),
-              "=r"(vm[9]), "=r"(vm[10]), "=r"(vm[11]), "=r"(vm[12]), "=r"(vm[13]), "=r"(vm[14]), "=r"(vm[15])
-            : "r"(acc_base + (uint32_t)c0) : "memory");
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(vc[0]), "=r"(vc[1]), "=r"(vc[2]), "=r"(vc[3]), "=r"(vc[4]), "=r"(vc[5]), "=r"(vc[6]), "=r"(vc[7]), "=r"(vc[8]),
-              "=r"(vc[9]), "=r"(vc[10]), "=r"(vc[11]), "=r"(vc[12]), "=r"(vc[13]), "=r"(vc[14]), "=r"(vc[15])
-            : "r"(acc_base + (uint32_t)(BN + c0)) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float f[16];
+      mbar_wait_t(bar_tfull + 8 * acc, acc_ph, timed && threadIdx.x == 64, w_t);
+      const long long te0 = (timed && threadIdx.x == 64) ? clock64() : 0;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int k = 0;
+      for (int u = cg; u < n_units; u += EP_GROUPS, ++k) {
+        const int sub = u / n_slabs, sl = u - sub * n_slabs;
+        const int oy0 = oy00 + sub * TH;
+        const int iy = oy0 + py0, ix = ox0 + px;
+        const bool valid = iy < p.Hy && ix < p.Wx;
+        const int oy = iy * p.out_stride + p.out_off_y, ox = ix * p.out_stride + p.out_off_x;
+        float* dst = p.y + ((((long long)n0 * p.Dout + z0) * p.Hout + oy) * p.Wout + ox) * (long long)p.Cs_out + p.c_off + cbase;
+        // the group's staging slab is free again once its previous TMA store has read it and its column sums are done
+        if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (cg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        const uint32_t acc_base = lane_base + (uint32_t)(acc * p.acc_stride + sub * 2 * BN);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(vc[j]), LO_INV, __uint_as_float(vm[j]));
-        if (p.bias) {
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = sl * 32 + half * 16;
+          if (c0 < BN) {
+            uint32_t vm[16], vc[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(vm[0]), "=r"(vm[1]), "=r"(vm[2]), "=r"(vm[3]), "=r"(vm[4]), "=r"(vm[5]), "=r"(vm[6]), "=r"(vm[7]), "=r"(vm[8]),
+                  "=r"(vm[9]), "=r"(vm[10]), "=r"(vm[11]), "=r"(vm[12]), "=r"(vm[13]), "=r"(vm[14]), "=r"(vm[15])
+                : "r"(acc_base + (uint32_t)c0) : "memory");
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(vc[0]), "=r"(vc[1]), "=r"(vc[2]), "=r"(vc[3]), "=r"(vc[4]), "=r"(vc[5]), "=r"(vc[6]), "=r"(vc[7]), "=r"(vc[8]),
+                  "=r"(vc[9]), "=r"(vc[10]), "=r"(vc[11]), "=r"(vc[12]), "=r"(vc[13]), "=r"(vc[14]), "=r"(vc[15])
+                : "r"(acc_base + (uint32_t)(BN + c0)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (c0 + j < n_here) f[j] += __ldg(p.bias + cbase + c0 + j);
-        }
-        if (p.leaky) {
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(vc[j]), LO_INV, __uint_as_float(vm[j]));
+            if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * 0.01f;
-        }
-        if (!valid) {
+              for (int j = 0; j < 16; ++j) if (c0 + j < n_here) f[j] += __ldg(p.bias + cbase + c0 + j);
+            }
+            if (p.leaky) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = 0.f;
-        } else if (c0 + 16 > n_here) {
+              for (int j = 0; j < 16; ++j) f[j] = f[j] >= 0.f ? f[j] : f[j] * 0.01f;
+            }
+            if (!valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (c0 + j >= n_here) f[j] = 0.f;
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+            } else if (c0 + 16 > n_here) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (c0 + j >= n_here) f[j] = 0.f;
+            }
+            if (tma_out || want_stats) {
+              uint8_t* rowp = ep + r * 128;
+              const int j0 = half * 4;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                *reinterpret_cast<float4*>(rowp + (((j0 + jj) ^ (r & 7)) << 4)) = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
+            }
+            if (valid && !tma_out && !(p.dev_flags & 32)) {
+              if (vec_ok && c0 + 16 <= n_here) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (c0 + j < n_here) dst[c0 + j] = f[j];
+              }
+            }
+          }
         }
         if (tma_out || want_stats) {
-          uint8_t* rowp = ep + (c0 >> 5) * 16384 + r * 128;
-          const int j0 = (c0 & 31) >> 2;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            *reinterpret_cast<float4*>(rowp + (((j0 + jj) ^ (r & 7)) << 4)) = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
-        }
-        if (valid && !tma_out && !(p.dev_flags & 32)) {
-          if (vec_ok && c0 + 16 <= n_here) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (c0 + j < n_here) dst[c0 + j] = f[j];
-          }
-        }
-        if (tma_out && ((c0 & 16) || c0 + 16 >= BN)) {       // last 16-column chunk of this 32-channel slab
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged slab -> visible to the TMA engine
           if (cg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-          const int sl = c0 >> 5;
-          if (storer && sl * 32 < n_here) {
-            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                         ::"l"((uint64_t)&tm_y), "r"(smem_base + stage_off + (uint32_t)(sl * 16384)), "r"(p.c_off + cbase + sl * 32), "r"(ox0), "r"(oy0), "r"(z0), "r"(n0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
         }
-      }
-      if (sub == nsub - 1) {
-        // every tcgen05.ld of this warp has completed (wait::ld above): hand the accumulator set back to the issuer
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      }
-      if (want_stats) {
-        asm volatile("bar.sync 3, %0;" ::"n"(128 * EP_GROUPS) : "memory");            // every slab staged
-        // column sums: the 256 epilogue threads split every column into row segments
-        const int e = cg * 128 + q * 32 + lane;
-        const int cw = (n_here + 31) & ~31;                       // columns rounded up to whole warps
-        const int nseg = cw <= 32 ? (128 * EP_GROUPS) / 32 : cw <= 64 ? (128 * EP_GROUPS) / 64 : cw <= 128 ? EP_GROUPS : 1;
-        const int seg_rows = 128 / nseg;
-        const int co = e % cw, seg = e / cw;
-        if (seg < nseg && co < n_here) {
-          const uint8_t* colp = ep + (co >> 5) * 16384 + (co & 3) * 4;
-          const int jc = (co & 31) >> 2;
-          float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
+        if (storer && sl * 32 < n_here) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"((uint64_t)&tm_y), "r"(ep_addr), "r"(p.c_off + cbase + sl * 32), "r"(ox0), "r"(oy0), "r"(z0), "r"(n0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (want_stats) {
+          const int co = sl * 32 + s_col;              // this thread's column of the slab, rows [32 s_seg, +32)
+          if (co < n_here) {
+            const uint8_t* colp = ep + (s_col & 3) * 4;
+            const int jc = s_col >> 2;
+            float s1 = 0.f, s2 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll 4
-          for (int rr = seg * seg_rows; rr < (seg + 1) * seg_rows; rr += 2) {
-            const float x0 = *reinterpret_cast<const float*>(colp + rr * 128 + ((jc ^ (rr & 7)) << 4));
-            const float x1 = *reinterpret_cast<const float*>(colp + (rr + 1) * 128 + ((jc ^ ((rr + 1) & 7)) << 4));
-            s1 += x0; s2 = fmaf(x0, x0, s2);
-            t1 += x1; t2 = fmaf(x1, x1, t2);
+            for (int rr = s_seg * 32; rr < s_seg * 32 + 32; rr += 2) {
+              const float x0 = *reinterpret_cast<const float*>(colp + rr * 128 + ((jc ^ (rr & 7)) << 4));
+              const float x1 = *reinterpret_cast<const float*>(colp + (rr + 1) * 128 + ((jc ^ ((rr + 1) & 7)) << 4));
+              s1 += x0; s2 = fmaf(x0, x0, s2);
+              t1 += x1; t2 = fmaf(x1, x1, t2);
+            }
+            const int col = cbase + co;
+            if ((k & 1) == 0) {
+              if (sa_col != col) {                       // another column: flush the previous one's sums
+                if (sa_col >= 0) { atomicAdd(p.stats + sa_col, sa1); atomicAdd(p.stats + p.Cout + sa_col, sa2); }
+                sa_col = col; sa1 = 0.0; sa2 = 0.0;
+              }
+              sa1 += (double)(s1 + t1); sa2 += (double)(s2 + t2);
+            } else {
+              if (sb_col != col) {
+                if (sb_col >= 0) { atomicAdd(p.stats + sb_col, sb1); atomicAdd(p.stats + p.Cout + sb_col, sb2); }
+                sb_col = col; sb1 = 0.0; sb2 = 0.0;
+              }
+              sb1 += (double)(s1 + t1); sb2 += (double)(s2 + t2);
+            }
           }
-          if (st_col != cbase + co) {                 // Cout chunk changed: flush the previous column's sums
-            if (st_col >= 0) { atomicAdd(p.stats + st_col, st1); atomicAdd(p.stats + p.Cout + st_col, st2); }
-            st_col = cbase + co; st1 = 0.0; st2 = 0.0;
-          }
-          st1 += (double)(s1 + t1); st2 += (double)(s2 + t2);
         }
       }
-     }   // sub-tiles
+      // every tcgen05.ld of this warp has completed (wait::ld above): hand the accumulator set back to the issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (timed && threadIdx.x == 64) t_ep += clock64() - te0;
       if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
-    if (st_col >= 0) { atomicAdd(p.stats + st_col, st1); atomicAdd(p.stats + p.Cout + st_col, st2); }
+    if (sa_col >= 0) { atomicAdd(p.stats + sa_col, sa1); atomicAdd(p.stats + p.Cout + sa_col, sa2); }
+    if (sb_col >= 0) { atomicAdd(p.stats + sb_col, sb1); atomicAdd(p.stats + p.Cout + sb_col, sb2); }
     if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the stores' reads
     if (dbg && threadIdx.x == 64) { dbg[5] = clock64(); dbg[4] = w_t; dbg[15] = t_ep; }
   }
@@ -695,7 +706,7 @@ int launch_h2(const __half* x_hi, const __half* x_lo, int N, int Din, int Hin, i
   p.acc_stride = 2 * p.BN * p.msub;
   int cols = 32; while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
-  p.staging_bytes = (uint32_t)((p.BN + 31) / 32) * 16384u;
+  p.staging_bytes = 2u * 16384u;            // one 32-channel output slab per epilogue group
   const size_t budget = 232448 - 512 - p.staging_bytes;
   int stages_a = p.msub > 1 ? 2 : 3;
   if ((size_t)stages_a * p.a_stage_bytes + 3 * (size_t)p.b_tile_bytes > budget) stages_a = 2;

@@ -88,6 +88,7 @@ struct nrgbd_kvnet {
   Pool pool;
   double* stats = nullptr;          // [2][512] per-channel sums of the conv in flight
   double* stats_b = nullptr;        // second set: a conv that consumes one BatchNorm (fused) while producing the next
+  unsigned int* bn_counter = nullptr;   // f16-pair mode: the BatchNorm pass re-zeroes the statistics it consumed (no memset nodes)
   int fuse_bn = 1;                  // 1: fold BasicBlock's first BN+ReLU into the second conv where planes >= 64 (tensor path); 2: everywhere
   float* scale = nullptr;           // [512]
   float* shift = nullptr;           // [512]
@@ -287,7 +288,7 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
   if (dst) y = *dst; else y = acquire(e, x.N, x.D, Ho, Wo, Cout, out_Cs);
   float* b = bias_name ? param(e, bias_name) : nullptr;
   if (e->rc) return y;
-  if (want_stats) cudaMemsetAsync(stats_buf, 0, sizeof(double) * 2 * Cout, e->st);
+  if (want_stats && e->conv_math != 2) cudaMemsetAsync(stats_buf, 0, sizeof(double) * 2 * Cout, e->st);   // f16-pair mode: kept zero by the BN pass
   const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
   char tag[56];
   snprintf(tag, sizeof(tag), "conv%dd k%d s%d d%d %d->%d %dx%dx%dx%d", kd > 1 ? 3 : 2, k, stride, dil, x.C, Cout, x.N, x.D, Ho, Wo);
@@ -349,15 +350,18 @@ Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k
   float* rm = e->bn_update_running ? param_opt(e, pre + ".1.running_mean") : nullptr;
   float* rv = e->bn_update_running ? param_opt(e, pre + ".1.running_var") : nullptr;
   if (e->rc) return y;
-  if (out_use && use_h2(e, y)) {
-    PairBuf pb;
-    pb.hi = e->pool.acquire((size_t)y.floats() * 2);
-    pb.lo = e->pool.acquire((size_t)y.floats() * 2);
-    if (!pb.hi || !pb.lo) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return y; }
+  if (e->conv_math == 2) {
+    const bool pair = out_use && use_h2(e, y);
+    PairBuf pb; pb.hi = pb.lo = nullptr;
+    if (pair) {
+      pb.hi = e->pool.acquire((size_t)y.floats() * 2);
+      pb.lo = e->pool.acquire((size_t)y.floats() * 2);
+      if (!pb.hi || !pb.lo) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return y; }
+    }
     ENG_CALL(e, nrgbd_bn_apply_stats_pair(y.p, e->stats, (double)y.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
-                                          0.1f, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, out_use == 2 ? nullptr : y.p,
-                                          pb.hi, pb.lo, (nrgbd_stream_t)e->st));
-    e->pairs[y.p] = pb;
+                                          0.1f, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, (pair && out_use == 2) ? nullptr : y.p,
+                                          pb.hi, pb.lo, e->bn_counter, (nrgbd_stream_t)e->st));
+    if (pair) e->pairs[y.p] = pb;
     return y;
   }
   ENG_CALL(e, nrgbd_bn_apply_stats(y.p, e->stats, (double)y.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
@@ -390,6 +394,10 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
     float* rm = e->bn_update_running ? param_opt(e, pre + ".downsample.1.running_mean") : nullptr;
     float* rv = e->bn_update_running ? param_opt(e, pre + ".downsample.1.running_var") : nullptr;
     if (!e->rc) {
+      if (e->conv_math == 2)
+        ENG_CALL(e, nrgbd_bn_apply_stats_pair(sc.p, e->stats, (double)sc.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
+                                              0.1f, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, nullptr, nullptr, e->bn_counter, (nrgbd_stream_t)e->st));
+      else
       ENG_CALL(e, nrgbd_bn_apply_stats(sc.p, e->stats, (double)sc.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
                                        0.1f, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, (nrgbd_stream_t)e->st));
     }
@@ -642,6 +650,7 @@ int nrgbd_kvnet_create(int H, int W, int D, int V, int feature_dim, int kv_featu
   const size_t hw = (size_t)e->h * e->w;
   bool ok = cudaMalloc((void**)&e->stats, sizeof(double) * 2 * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->stats_b, sizeof(double) * 2 * 512) == cudaSuccess &&
+            cudaMalloc((void**)&e->bn_counter, sizeof(unsigned int)) == cudaSuccess &&
             cudaMalloc((void**)&e->scale, sizeof(float) * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->shift, sizeof(float) * 512) == cudaSuccess &&
             cudaMalloc((void**)&e->ws_sweep, sizeof(float) * 12 * V) == cudaSuccess &&
@@ -651,6 +660,7 @@ int nrgbd_kvnet_create(int H, int W, int D, int V, int feature_dim, int kv_featu
             cudaMalloc((void**)&e->depth, sizeof(float) * hw) == cudaSuccess &&
             cudaMalloc((void**)&e->conf, sizeof(float) * hw) == cudaSuccess;
   if (!ok) { nrgbd_set_error("nrgbd_kvnet_create: cudaMalloc failed"); delete e; return NRGBD_ERR_NOMEM; }
+  cudaMemset(e->stats, 0, sizeof(double) * 2 * 512); cudaMemset(e->stats_b, 0, sizeof(double) * 2 * 512); cudaMemset(e->bn_counter, 0, sizeof(unsigned int));
   *out = e;
   return NRGBD_OK;
 }
@@ -662,7 +672,7 @@ int nrgbd_kvnet_destroy(nrgbd_kvnet* e) {
   for (auto& kv : e->packed_tc) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
   for (auto& kv : e->packed_h2) cudaFree(kv.second.w);
   for (int i = 0; i < 2; ++i) { cudaFree(e->cam[i].K); cudaFree(e->cam[i].rays); }
-  cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->stats_b); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
+  cudaFree(e->d_planes); cudaFree(e->stats); cudaFree(e->stats_b); cudaFree(e->bn_counter); cudaFree(e->scale); cudaFree(e->shift); cudaFree(e->ws_sweep);
   cudaFree(e->bv_cur_hwd); cudaFree(e->dpv_hwd); cudaFree(e->prior_hwd); cudaFree(e->depth); cudaFree(e->conf);
   cudaFree(e->x0_buf); cudaFree(e->rt_buf); cudaFree(e->ref_cur_hwd); cudaFree(e->ref_kv_hwd);
   drop_graphs(e);
@@ -744,7 +754,10 @@ int nrgbd_kvnet_set_option(nrgbd_kvnet* e, const char* key, int value) {
   if (k == "use_graph") { drop_graphs(e); e->use_graph = value; return NRGBD_OK; }
   if (k == "conv_math") {            // 0: exact fp32 (CUDA cores); 1: tcgen05 3xTF32; 2: tcgen05 split-fp16 pairs
     if (value < 0 || value > 2) { nrgbd_set_error("conv_math must be 0 (fp32), 1 (tf32x3) or 2 (f16x3)"); return NRGBD_ERR_BAD_ARG; }
-    drop_graphs(e); e->conv_math = value; return NRGBD_OK;
+    drop_graphs(e); e->conv_math = value;
+    // f16-pair mode keeps the statistics buffers zero between uses (the BatchNorm pass re-zeroes what it consumed)
+    cudaMemset(e->stats, 0, sizeof(double) * 2 * 512); cudaMemset(e->stats_b, 0, sizeof(double) * 2 * 512); cudaMemset(e->bn_counter, 0, sizeof(unsigned int));
+    return NRGBD_OK;
   }
   nrgbd_set_error("nrgbd_kvnet_set_option: unknown option '%s'", key);
   return NRGBD_ERR_BAD_ARG;

@@ -10,8 +10,10 @@ Same names and argument order as the reference:
     depth_regression(Depth_Indx_vol, BV)
     export_res_img(ref_dat, BV_measure, d_candi, resfldr, batch_idx, depth_scale=1000, conf_scale=1000)
     export_res_refineNet(ref_dat, BV_measure, d_candi, res_fldr, batch_idx, ...)
-The matplotlib composites of export_res_refineNet (colour-mapped previews, :117-141) are written
-only when matplotlib is importable; the numeric products (.mat, 16-bit depth, maps) always are.
+The matplotlib previews of export_res_refineNet (input.png, conf.png, dmap_raw.png, dmaps_diff.png, dmap_ref.png and
+their concatenation res_%05d.png, :104-141) are written by `_previews` when matplotlib is importable, exactly as the reference
+needs it; without matplotlib (this image) that group is omitted - the numeric products (.mat, .pgm, 16-bit PNGs) always are.
+rgb_%05d.png has the reference's cv2 (BGR) byte order.
 """
 import ctypes
 import os
@@ -99,6 +101,31 @@ def export_res_img(ref_dat, BV_measure, d_candi, resfldr, batch_idx, depth_scale
     write_pgm16('%s/conf_%05d.pgm' % (resfldr, batch_idx), _u16_host(maps['conf_u16']))
 
 
+def _previews(resfldr, batch_idx, img_in_raw, conf, dmap, dmap_ref, d_max, diff_vrange_ratio):
+    """The colour-mapped preview files of export_res.py:104-141 (input.png, conf.png, dmap_raw.png, [dmaps_diff.png,
+    dmap_ref.png] and their horizontal concatenation res_%05d.png). They need matplotlib, as in the reference; when it is not
+    importable NOTHING of this group is written (the numeric products - .mat, .pgm, 16-bit PNGs - do not depend on it)."""
+    try:
+        import matplotlib as mlt
+        mlt.use('Agg')
+        import matplotlib.pyplot as plt
+        import PIL.Image as image
+    except ImportError:
+        return False
+    img_in = (img_in_raw - img_in_raw.min()) / (img_in_raw.max() - img_in_raw.min()) * 255.
+    names = ['%s/input.png' % resfldr, '%s/conf.png' % resfldr, '%s/dmap_raw.png' % resfldr]
+    if dmap_ref is not None:
+        mask = (dmap_ref > 0).astype(np.float64)
+        plt.imsave('%s/dmaps_diff.png' % resfldr, np.abs(dmap_ref - dmap) * mask, vmin=0, vmax=d_max / diff_vrange_ratio)
+        plt.imsave('%s/dmap_ref.png' % resfldr, dmap_ref, vmax=d_max, vmin=0, cmap='gray')
+        names += ['%s/dmaps_diff.png' % resfldr, '%s/dmap_ref.png' % resfldr]
+    plt.imsave(names[1], conf, vmin=0, vmax=1, cmap='jet')
+    plt.imsave(names[2], dmap, vmin=0., vmax=d_max, cmap='gray')
+    plt.imsave(names[0], img_in.astype(np.uint8))
+    plt.imsave('%s/res_%05d.png' % (resfldr, batch_idx), np.hstack([np.array(image.open(n)) for n in names]))      # cat_imgs :30-33
+    return True
+
+
 def export_res_refineNet(ref_dat, BV_measure, d_candi, res_fldr, batch_idx, diff_vrange_ratio=4,
                          cam_pose=None, cam_intrinM=None, output_pngs=False, save_mat=True, output_dmap_ref=True):
     """export_res.py:77-160: depth / confidence maps of the refined DPV, .mat dump and optional 16-bit PNGs."""
@@ -110,9 +137,10 @@ def export_res_refineNet(ref_dat, BV_measure, d_candi, res_fldr, batch_idx, diff
     dmap_ref = None
     if output_dmap_ref:
         dmap_ref = ref_dat['dmap_imgsize'].squeeze().cpu().numpy()
+    _previews(res_fldr, batch_idx, img_in_raw, confMap_log, dmap, dmap_ref, float(np.max(d_candi)), diff_vrange_ratio)
     if save_mat:
         import scipy.io as sio
-        mdict = {'dmap': dmap, 'img': img_in_raw, 'confMap': confMap_log, 'img_path': ref_dat.get('img_path', '')}
+        mdict = {'dmap': dmap, 'img': img_in_raw, 'confMap': confMap_log, 'img_path': ref_dat['img_path']}      # KeyError as in the reference (:119)
         if output_dmap_ref:
             mdict['dmap_ref'] = dmap_ref
             if cam_pose is not None:
@@ -125,7 +153,8 @@ def export_res_refineNet(ref_dat, BV_measure, d_candi, res_fldr, batch_idx, diff
         try:
             import PIL.Image as image
             image.fromarray(_u16_host(maps['dmap_u16'])).save('%s/d_%05d.png' % (png_fldr, batch_idx))
-            image.fromarray((_un_normalize(img_in_raw) * 255).astype(np.uint8)).save('%s/rgb_%05d.png' % (png_fldr, batch_idx))
+            # the reference writes this RGB array with cv2.imwrite, which stores it as if it were BGR (:152): same file contents here
+            image.fromarray(np.ascontiguousarray((_un_normalize(img_in_raw) * 255).astype(np.uint8)[:, :, ::-1])).save('%s/rgb_%05d.png' % (png_fldr, batch_idx))
             image.fromarray(_u16_host(maps['conf_u16']).astype(np.uint8)).save('%s/conf_%05d.png' % (png_fldr, batch_idx))
             if output_dmap_ref:
                 image.fromarray((dmap_ref * 1000).astype(np.uint16)).save('%s/dref_%05d.png' % (png_fldr, batch_idx))

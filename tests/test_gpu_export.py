@@ -87,3 +87,31 @@ def test_export_full_size_properties():
     mu = X.depth_conf_maps(uni, d_candi)
     assert abs(float(mu['dmap'][0, 0]) - float(d_candi.mean())) <= 1e-5
     assert int(mu['conf_u16'][0, 0].cpu().numpy().view(np.uint16)) == int(np.float32(np.exp(np.float32(np.log(1.0 / D)))) * np.float32(1000))
+
+
+def test_export_res_refineNet_products(tmp_path):
+    """export_res.py:77-160 mirror: .mat contents, 16-bit depth PNG, cv2 (BGR) byte order of rgb_*.png, KeyError on a frame dict
+    without 'img_path' (the reference indexes it), previews only with matplotlib."""
+    import scipy.io as sio
+    import PIL.Image as image
+    from neuralrgbd_b200.test_utils import export_res as X
+    bv, d_candi, img = cases.export_case('export_48x64_d16')
+    ref_dat = {'img': torch.from_numpy(img), 'img_path': 'scene0000/frame-000010.color.jpg'}
+    dmap, conf = X.export_res_refineNet(ref_dat, torch.from_numpy(bv).cuda(), d_candi, str(tmp_path), 7, output_pngs=True, save_mat=True,
+                                        output_dmap_ref=False)
+    od, oc, od16, _ = E.export_maps(bv[0], d_candi)
+    assert np.max(np.abs(dmap - od) / np.abs(od)) <= 1e-6 and np.max(np.abs(conf - oc) / oc) <= 1e-6
+    m = sio.loadmat(str(tmp_path / 'depth_00007.mat'))
+    assert np.array_equal(m['dmap'], dmap) and np.array_equal(m['confMap'], conf) and m['img_path'][0] == ref_dat['img_path']
+    d_png = np.array(image.open(str(tmp_path / 'output_pngs' / 'd_00007.png')))
+    assert np.abs(d_png.astype(np.int64) - od16.astype(np.int64)).max() <= 1
+    rgb = np.array(image.open(str(tmp_path / 'output_pngs' / 'rgb_00007.png')))
+    want = (X._un_normalize(img[0].transpose(1, 2, 0)) * 255).astype(np.uint8)
+    assert np.array_equal(rgb[:, :, ::-1], want)                       # decoded R channel = the array's B channel, as cv2.imwrite leaves it
+    try:
+        import matplotlib      # noqa: F401
+        assert (tmp_path / 'res_00007.png').exists() and (tmp_path / 'conf.png').exists()
+    except ImportError:
+        assert not (tmp_path / 'res_00007.png').exists()
+    with pytest.raises(KeyError):
+        X.export_res_refineNet({'img': torch.from_numpy(img)}, torch.from_numpy(bv).cuda(), d_candi, str(tmp_path), 8, output_dmap_ref=False)

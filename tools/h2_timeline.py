@@ -48,14 +48,16 @@ L.nrgbd_dev_conv_h2_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
 run(); torch.cuda.synchronize()
 L.nrgbd_dev_conv_h2_set_debug_buffer(None)
 t = dbg.cpu().numpy().astype(np.float64)
-items = ny * tiles / n_cta
-steps = kd * k * k * (cin_p // 32)
+msub = 4 if bn <= 32 else 2 if bn <= 64 else 1
+G = 3 if (k * k) % 3 == 0 else 1
+items = ny * N * D * ((Ho + 16 * msub - 1) // (16 * msub)) * ((Wo + 7) // 8) / n_cta
+steps = kd * (k * k // G) * (cin_p // 32)
 seg = {'setup': t[:, 1] - t[:, 0], 'lifetime': t[:, 6] - t[:, 0], 'issuer_done_at': t[:, 3] - t[:, 0], 'producer_done_at': t[:, 8] - t[:, 0],
        'epilogue_done_at': t[:, 5] - t[:, 0],
        'issuer_main_loops_total': t[:, 14], 'issuer_wait_a_full': t[:, 11], 'issuer_wait_b_full': t[:, 12], 'issuer_wait_acc_free': t[:, 13],
        'producer_wait_a_empty': t[:, 9], 'producer_wait_b_empty': t[:, 10], 'epilogue_wait_acc_full': t[:, 4], 'epilogue_busy': t[:, 15]}
 out = {kk: {'mean': float(v.mean()), 'p90': float(np.percentile(v, 90))} for kk, v in seg.items()}
-out['items_per_cta'] = items; out['steps_per_item'] = steps; out['BN'] = bn
+out['items_per_cta'] = items; out['steps_per_item'] = steps; out['BN'] = bn; out['mma_per_step'] = 4 * msub * G
 out['cycles_per_step_in_main_loop'] = float(t[:, 14].mean() / (items * steps))
 out['lifetime_per_item'] = float((t[:, 6] - t[:, 0]).mean() / items)
 print(json.dumps({'shape': a, 'segments': out}, indent=1))
