@@ -82,5 +82,5 @@ def test_pose_refinement_step_reduces_the_photometric_loss():
         loss = torch.nn.functional.l1_loss(warped * mask, target * mask)
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < 0.6 * losses[0], losses[::8]
