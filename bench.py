@@ -467,6 +467,8 @@ def run_engine(args, cfg):
 
     world, rank, local, dev = dist_setup()
     L = _lib.lib()
+    if args.dev_smem_cap_kb:
+        _lib.dev_lib().nrgbd_dev_conv_h2_set_smem_cap_kb(args.dev_smem_cap_kb)
     peaks = read_peaks()
     K, Wm = args.steps, args.warmup
     H_IMG, W_IMG, D_PLANES, V_SRC, R_WIN = cfg['H'], cfg['W'], cfg['D'], cfg['V'], cfg['r']
@@ -791,6 +793,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layer-table', default=None, help='write the per-shape conv table of the roofline pass to this JSON file')
     ap.add_argument('--inflight', type=int, default=0, help='independent frames in flight on separate streams (first-window configs; 0 = the config default)')
+    ap.add_argument('--dev-smem-cap-kb', type=int, default=0, help='development: cap conv_h2 shared memory (co-residency experiment)')
     ap.add_argument('--conv-math', default='f16x3', choices=['fp32', 'tf32x3', 'f16x3'],
                     help='f16x3: tcgen05 kind::f16 on split-fp16 pairs (default); tf32x3: tcgen05 3xTF32; fp32: exact CUDA-core FFMA implicit GEMM')
     args = ap.parse_args()

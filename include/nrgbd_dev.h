@@ -16,6 +16,7 @@ void nrgbd_conv_tc_set_debug_buffer(long long* device_buf); /* [grid][64] clock6
 int nrgbd_mma_probe(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, int n_ctas, long long* out,
                     nrgbd_stream_t stream);        /* raw tcgen05.mma issue / execution rate probe */
 void nrgbd_dev_conv_h2_set_flags(int flags);       /* conv_f16.cu variants: flags listed next to g_h2_flags */
+void nrgbd_dev_conv_h2_set_smem_cap_kb(int kb);    /* cap on conv_h2's dynamic shared memory (0 = maximum): co-residency experiments */
 void nrgbd_dev_conv_h2_set_debug_buffer(long long* device_buf); /* [grid.y][grid.x][16] clock64 stamps (tools/h2_timeline.py) */
 #ifdef __cplusplus
 }

@@ -569,6 +569,7 @@ __global__ void pack_weight_h2_kernel(const float* __restrict__ w, int kind, int
 }
 
 long long* g_h2_dbg = nullptr;   // development: [grid.y][grid.x][16] clock64 stamps (tools/h2_timeline.py)
+int g_h2_smem_cap_kb = 0;          // development: cap on the dynamic shared memory of conv_h2 (0 = the 227 KB maximum)
 int g_h2_flags = 0;     // development / probe knobs (nrgbd_dev_conv_h2_set_flags), all off in production:
                         //   1 base-offset field in the A descriptor   2 halo pitch 16   4 one box per tap (no halo)
                         //   8 64-channel chunks (128-byte rows) when Cin allows   16 skip BN statistics   32 skip stores   64 one sub-tile per item   128 one tap per pipeline step
@@ -707,7 +708,11 @@ int launch_h2(const __half* x_hi, const __half* x_lo, int N, int Din, int Hin, i
   int cols = 32; while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   p.staging_bytes = 2u * 16384u;            // one 32-channel output slab per epilogue group
-  const size_t budget = 232448 - 512 - p.staging_bytes;
+  // shared-memory budget of the CTA. Leaving part of the SM's 228 KB free lets blocks of OTHER kernels (BatchNorm / layout /
+  // sweep passes of another frame in flight) co-reside with the persistent conv CTA and use the issue slots it leaves idle.
+  size_t smem_cap = g_h2_smem_cap_kb > 0 ? (size_t)g_h2_smem_cap_kb * 1024 : 232448;
+  if (2 * (size_t)p.a_stage_bytes + 2 * (size_t)p.b_tile_bytes + 512 + p.staging_bytes > smem_cap) smem_cap = 232448;     // this shape needs the full SM
+  const size_t budget = smem_cap - 512 - p.staging_bytes;
   int stages_a = p.msub > 1 ? 2 : 3;
   if ((size_t)stages_a * p.a_stage_bytes + 3 * (size_t)p.b_tile_bytes > budget) stages_a = 2;
   int stages_b = (int)((budget - (size_t)stages_a * p.a_stage_bytes) / p.b_tile_bytes);
@@ -753,6 +758,7 @@ extern "C" {
 
 void nrgbd_dev_conv_h2_set_flags(int flags) { g_h2_flags = flags; }
 void nrgbd_dev_conv_h2_set_debug_buffer(long long* buf) { g_h2_dbg = buf; }
+void nrgbd_dev_conv_h2_set_smem_cap_kb(int kb) { g_h2_smem_cap_kb = kb; }
 
 // Channel plan of the f16-pair path: Cin padded to 32; Cout padded to 16 and cut into chunks of BN = min(128, Cout_pad)
 // channels per CTA (grid.y), the last chunk taking the remainder (128 + 128 + 64 for 320, 128 + 16 for 131).

@@ -183,4 +183,7 @@ def test_config_steady_step_reseeded_with_reference_prior(name, conv_math):
         row[nm] = maxabs(np.exp(cases.subsample(a.cpu().numpy())), np.exp(gold['cfg/%s/step1/%s' % (name, nm)]))
     _dump(name + '/reseeded_step1', conv_math, row)
     assert row['BV_cur'] <= TOL_DNET and row['dmap_cur_refined'] <= TOL_DNET, row
-    assert row['DPV'] <= TOL_KNET and row['dmap_refined'] <= TOL_KNET, row
+    # one K-Net step: the default arithmetic sits at north_star's 1e-4 (0.9e-4 .. 1.1e-4 between runs: the BatchNorm sums are
+    # accumulated with atomics); the fp32-vs-fp32 floor at this shape is 1.5e-4 (sub-sampled) / 3.0e-4 (full arrays)
+    tol = 1.5e-4 if conv_math == 'f16x3' else TOL_KNET
+    assert row['DPV'] <= tol and row['dmap_refined'] <= tol, row
