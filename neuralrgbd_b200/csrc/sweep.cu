@@ -184,7 +184,10 @@ plane_sweep_kernel(const float4* __restrict__ ref_w, const float4* __restrict__ 
 // epilogue either stores the raw cost (est_swp_volume_v4 mirror) or finishes the D-Net head in place:
 // BV = log_softmax(-cost) (models/basic.py:299-300), expected depth sum exp(BV) d and confidence max exp(BV).
 // ---------------------------------------------------------------------------------------------------------------
-template <int PASSES, bool L1, int NB>      // NB = ceil(D / 16) plane batches (register-resident totals)
+// LANES threads per reference pixel (each PASSES float4 channel slices), NB = ceil(D / LANES) plane batches. With 8 lanes
+// and two slices per lane (64 channels) the per-plane overhead - corner record, reuse test, reduction, loop - is spread over
+// twice the arithmetic of the 16-lane form.
+template <int LANES, int PASSES, bool L1, int NB>
 __global__ void __launch_bounds__(256)
 plane_sweep2_kernel(const float4* __restrict__ ref_w, const float4* __restrict__ src_w, int G,
                     const float4* __restrict__ ref_n, const float4* __restrict__ src_n,
@@ -192,10 +195,9 @@ plane_sweep2_kernel(const float4* __restrict__ ref_w, const float4* __restrict__
                     const float* __restrict__ rays, const float* __restrict__ dpl, int V, int D, int w,
                     int h, float cx, float cy, float sigma, float* __restrict__ cost, float* __restrict__ bv,
                     float* __restrict__ depth, float* __restrict__ conf) {
-  constexpr int LANES = 16;
   constexpr int GROUPS_PER_BLOCK = 256 / LANES;
   __shared__ TapRec recs[256];
-  // per-plane totals: thread t owns s_tot[b][t] (plane 16 b + lane of its pixel). Kept in shared memory so that the batch
+  // per-plane totals: thread t owns s_tot[b][t] (plane LANES b + lane of its pixel). Kept in shared memory so that the batch
   // loop can stay ROLLED: fully unrolled over the NB batches the kernel was instruction-fetch bound (ncu: 2.5 "no
   // instruction" stall cycles per issue with ~80 KB of code)
   __shared__ float s_tot[NB][256];
@@ -336,17 +338,24 @@ plane_sweep2_kernel(const float4* __restrict__ ref_w, const float4* __restrict__
 }
 
 template <bool L1>
-int launch_sweep2(int passes, int D, dim3 grid, cudaStream_t st, const float4* ref_w, const float4* src_w, int G, const float4* ref_n,
+int launch_sweep2(int G, int D, int hw, cudaStream_t st, const float4* ref_w, const float4* src_w, const float4* ref_n,
                   const float4* src_n, const float* t1, const float* KR, const float* rays, const float* dpl, int V, int w, int h, float cx,
                   float cy, float sigma, float* cost, float* bv, float* depth, float* conf) {
+#define NRGBD_SWEEP2(LN, P, NBV)                                                                                                   \
+  plane_sweep2_kernel<LN, P, L1, NBV><<<ceil_div((long long)hw * LN, 256), 256, 0, st>>>(ref_w, src_w, G, ref_n, src_n, t1, KR, rays, dpl, \
+                                                                                        V, D, w, h, cx, cy, sigma, cost, bv, depth, conf)
+  if (G == 16 && (long long)hw * D >= (8ll << 20)) {      // 64 wide channels, large volumes: 8 lanes x 2 slices (measured: -12 % at 270x480x256x8,
+                                                           // +15 % at 120x160x64x4 where the lower occupancy costs more than the overhead saves)
+    const int nb = (D + 7) / 8;
+    if (nb <= 4) NRGBD_SWEEP2(8, 2, 4); else if (nb <= 8) NRGBD_SWEEP2(8, 2, 8); else if (nb <= 16) NRGBD_SWEEP2(8, 2, 16); else NRGBD_SWEEP2(8, 2, 32);
+    return NRGBD_OK;
+  }
+  const int passes = ceil_div(G, 16);  // 16 lanes
   const int nb = (D + 15) / 16;
-#define NRGBD_SWEEP2(P, NBV)                                                                                                     \
-  plane_sweep2_kernel<P, L1, NBV><<<grid, 256, 0, st>>>(ref_w, src_w, G, ref_n, src_n, t1, KR, rays, dpl, V, D, w, h, cx, cy, sigma, \
-                                                        cost, bv, depth, conf)
   if (passes == 1) {
-    if (nb <= 2) NRGBD_SWEEP2(1, 2); else if (nb <= 4) NRGBD_SWEEP2(1, 4); else if (nb <= 8) NRGBD_SWEEP2(1, 8); else NRGBD_SWEEP2(1, 16);
+    if (nb <= 2) NRGBD_SWEEP2(16, 1, 2); else if (nb <= 4) NRGBD_SWEEP2(16, 1, 4); else if (nb <= 8) NRGBD_SWEEP2(16, 1, 8); else NRGBD_SWEEP2(16, 1, 16);
   } else if (passes == 2) {
-    if (nb <= 2) NRGBD_SWEEP2(2, 2); else if (nb <= 4) NRGBD_SWEEP2(2, 4); else if (nb <= 8) NRGBD_SWEEP2(2, 8); else NRGBD_SWEEP2(2, 16);
+    if (nb <= 2) NRGBD_SWEEP2(16, 2, 2); else if (nb <= 4) NRGBD_SWEEP2(16, 2, 4); else if (nb <= 8) NRGBD_SWEEP2(16, 2, 8); else NRGBD_SWEEP2(16, 2, 16);
   } else {
     return NRGBD_ERR_UNSUPPORTED;
   }
@@ -479,12 +488,8 @@ static int sweep_impl(const float* ref_wide, const float* ref_narrow, const floa
   const bool fused_head = bv_hwd || depth || conf;
   if (G >= 16 && G <= 32 && D <= 256) {
     // register-cached corners (plane_sweep2_kernel), optional fused D-Net head
-    dim3 grid(ceil_div((long long)hw * 16, 256));
-    const int passes = ceil_div(G, 16);
-    int rc = metric == 0 ? launch_sweep2<false>(passes, D, grid, st, rw, sw, G, rn, sn, t1, KR, rays, d_planes, V, w, h, cx, cy, sigma, cost_hwd,
-                                                bv_hwd, depth, conf)
-                         : launch_sweep2<true>(passes, D, grid, st, rw, sw, G, rn, sn, t1, KR, rays, d_planes, V, w, h, cx, cy, sigma, cost_hwd,
-                                               bv_hwd, depth, conf);
+    int rc = metric == 0 ? launch_sweep2<false>(G, D, hw, st, rw, sw, rn, sn, t1, KR, rays, d_planes, V, w, h, cx, cy, sigma, cost_hwd, bv_hwd, depth, conf)
+                         : launch_sweep2<true>(G, D, hw, st, rw, sw, rn, sn, t1, KR, rays, d_planes, V, w, h, cx, cy, sigma, cost_hwd, bv_hwd, depth, conf);
     if (rc == NRGBD_OK) { NRGBD_COUNT(2); NRGBD_LAUNCH_CHECK(); return NRGBD_OK; }
   }
   NRGBD_REQUIRE(cost_hwd || !fused_head, "this channel configuration needs a cost buffer (the fused head runs as a second pass)");
