@@ -467,6 +467,8 @@ def run_engine(args, cfg):
 
     world, rank, local, dev = dist_setup()
     L = _lib.lib()
+    if args.dev_bn_unroll:
+        _lib.dev_lib().nrgbd_dev_set_bn_unroll(args.dev_bn_unroll)
     if args.dev_smem_cap_kb:
         _lib.dev_lib().nrgbd_dev_conv_h2_set_smem_cap_kb(args.dev_smem_cap_kb)
     peaks = read_peaks()
@@ -793,6 +795,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layer-table', default=None, help='write the per-shape conv table of the roofline pass to this JSON file')
     ap.add_argument('--inflight', type=int, default=0, help='independent frames in flight on separate streams (first-window configs; 0 = the config default)')
+    ap.add_argument('--dev-bn-unroll', type=int, default=0, help='development: vectors in flight per thread in the BatchNorm pass')
     ap.add_argument('--dev-smem-cap-kb', type=int, default=0, help='development: cap conv_h2 shared memory (co-residency experiment)')
     ap.add_argument('--conv-math', default='f16x3', choices=['fp32', 'tf32x3', 'f16x3'],
                     help='f16x3: tcgen05 kind::f16 on split-fp16 pairs (default); tf32x3: tcgen05 3xTF32; fp32: exact CUDA-core FFMA implicit GEMM')
@@ -807,6 +810,9 @@ def main():
     global _emit
     _emit = lambda text: os.write(real_stdout, (text + '\n').encode())      # noqa: E731
     if args.impl == 'reference':
+        # the CPU arm must not see a GPU: with visible devices nn.DataParallel (test_KVNet.py:163) scatters the inputs to cuda:0
+        # while the .cuda() shim keeps everything else on the host
+        os.environ['CUDA_VISIBLE_DEVICES'] = ''
         run_reference(args, cfg, on_gpu=False)
     elif args.impl == 'reference-gpu':
         run_reference(args, cfg, on_gpu=True)

@@ -291,6 +291,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale, co
 // BatchNorm finalize + apply in one kernel: every block derives scale/shift for all C channels from
 // the accumulated statistics into shared memory (C <= 512), then streams its slice of the activation.
 // Block 0 also performs the training-mode running-statistics update.
+template <int U>
 __global__ void __launch_bounds__(256)
 bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ stats, double count,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -325,36 +326,53 @@ bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ st
       *done_counter = 0u;
     }
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)((i * 4) % Cs);
-    float4 v = reinterpret_cast<const float4*>(x)[i];
-    float o[4] = {v.x, v.y, v.z, v.w};
+  // four 16-byte vectors per thread and iteration, all loads issued before the first use: 64 (128 with a residual) bytes in
+  // flight per thread instead of 16 - this pass is pure streaming and was latency-bound with one vector per iteration
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 v[U], rr[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (c + k < C) {
-        float t = fmaf(o[k], s_scale[c + k], s_shift[c + k]);
-        if (relu) t = fmaxf(t, 0.f);
-        o[k] = t;
-      } else {
-        o[k] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        v[u] = reinterpret_cast<const float4*>(x)[i];
+        if (res) rr[u] = reinterpret_cast<const float4*>(res)[i];
       }
     }
-    if (res) {
-      float4 r = reinterpret_cast<const float4*>(res)[i];
-      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
-    }
-    if (y) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
-    if (y_hi) {                      // the consumer is an f16-pair convolution: emit its operand planes in the same pass
-      uint2 h, l;
-      nrgbd_split_pair4(o, h, l);
-      y_hi[i] = h; y_lo[i] = l;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) continue;
+      const int c = (int)((i * 4) % Cs);
+      float o[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c + k < C) {
+          float t = fmaf(o[k], s_scale[c + k], s_shift[c + k]);
+          if (relu) t = fmaxf(t, 0.f);
+          o[k] = t;
+        } else {
+          o[k] = 0.f;
+        }
+      }
+      if (res) { o[0] += rr[u].x; o[1] += rr[u].y; o[2] += rr[u].z; o[3] += rr[u].w; }
+      if (y) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+      if (y_hi) {                      // the consumer is an f16-pair convolution: emit its operand planes in the same pass
+        uint2 h, l;
+        nrgbd_split_pair4(o, h, l);
+        y_hi[i] = h; y_lo[i] = l;
+      }
     }
   }
 }
 
+int g_bn_unroll = 1;      // vectors in flight per thread in the BatchNorm pass (development knob, nrgbd_dev_set_bn_unroll)
+
 }  // namespace
 
 extern "C" {
+
+void nrgbd_dev_set_bn_unroll(int u) { g_bn_unroll = u; }
 
 int nrgbd_pack_conv_weight(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad, int Cout_pad,
                            float* out, cudaStream_t st) {
@@ -477,8 +495,8 @@ int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, cons
   long long n4 = n_pos * Cs / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_apply_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                         n4, Cs, C, y, nullptr, nullptr, nullptr, nullptr);
+  bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
+                                                            n4, Cs, C, y, nullptr, nullptr, nullptr, nullptr);
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;
@@ -496,9 +514,18 @@ int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const
   long long n4 = n_pos * Cs / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_apply_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                         n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
-                                                         rezero_counter ? stats : nullptr, rezero_counter);
+  if (g_bn_unroll == 4)
+    bn_apply_stats_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
+                                                              n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
+                                                              rezero_counter ? stats : nullptr, rezero_counter);
+  else if (g_bn_unroll == 2)
+    bn_apply_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
+                                                              n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
+                                                              rezero_counter ? stats : nullptr, rezero_counter);
+  else
+    bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
+                                                              n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
+                                                              rezero_counter ? stats : nullptr, rezero_counter);
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;

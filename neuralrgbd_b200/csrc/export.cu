@@ -38,33 +38,39 @@ export_depth_conf_kernel(const float* __restrict__ bv, const float* __restrict__
   float acc[VEC], m[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) { acc[k] = 0.f; m[k] = -INFINITY; }
-  int d = 0;
-  for (; d + 8 <= D; d += 8) {                 // eight independent loads in flight per thread (HBM latency)
-    float v[8][VEC];
+  // software pipeline: the loads of plane batch b + 1 are in flight while batch b is reduced (the block is a single wave:
+  // its run time is the sum of its batches' latencies, so they must overlap); sums stay sequential over the planes
+  constexpr int B = 8;
+  float cur[B][VEC], nxt[B][VEC];
+  auto load_batch = [&](float (&dst)[B][VEC], int d0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (VEC == 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(bv + (long long)(d + j) * HW + p));
-        v[j][0] = q.x; v[j][1 % VEC] = q.y; v[j][2 % VEC] = q.z; v[j][3 % VEC] = q.w;
-      } else {
-        v[j][0] = __ldg(bv + (long long)(d + j) * HW + p);
+    for (int j = 0; j < B; ++j) {
+      if (d0 + j < D) {
+        if (VEC == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(bv + (long long)(d0 + j) * HW + p));
+          dst[j][0] = q.x; dst[j][1 % VEC] = q.y; dst[j][2 % VEC] = q.z; dst[j][3 % VEC] = q.w;
+        } else {
+          dst[j][0] = __ldg(bv + (long long)(d0 + j) * HW + p);
+        }
       }
     }
+  };
+  load_batch(cur, 0);
+  for (int d = 0; d < D; d += B) {
+    if (d + B < D) load_batch(nxt, d + B);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < B; ++j)
+      if (d + j < D) {
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        acc[k] = __fadd_rn(acc[k], __fmul_rn(expf(v[j][k]), dc[d + j]));
-        m[k] = fmaxf(m[k], v[j][k]);
+        for (int k = 0; k < VEC; ++k) {
+          acc[k] = __fadd_rn(acc[k], __fmul_rn(expf(cur[j][k]), dc[d + j]));
+          m[k] = fmaxf(m[k], cur[j][k]);
+        }
       }
-  }
-  for (; d < D; ++d) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const float v = __ldg(bv + (long long)d * HW + p + k);
-      acc[k] = __fadd_rn(acc[k], __fmul_rn(expf(v), dc[d]));
-      m[k] = fmaxf(m[k], v);
-    }
+    for (int j = 0; j < B; ++j)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) cur[j][k] = nxt[j][k];
   }
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
