@@ -187,20 +187,20 @@ plane_sweep_kernel(const float4* __restrict__ ref_w, const float4* __restrict__ 
 // LANES threads per reference pixel (each PASSES float4 channel slices), NB = ceil(D / LANES) plane batches. With 8 lanes
 // and two slices per lane (64 channels) the per-plane overhead - corner record, reuse test, reduction, loop - is spread over
 // twice the arithmetic of the 16-lane form.
-template <int LANES, int PASSES, bool L1, int NB>
-__global__ void __launch_bounds__(256)
+template <int LANES, int PASSES, bool L1, int NB, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB)
 plane_sweep2_kernel(const float4* __restrict__ ref_w, const float4* __restrict__ src_w, int G,
                     const float4* __restrict__ ref_n, const float4* __restrict__ src_n,
                     const float* __restrict__ t1, const float* __restrict__ KR,
                     const float* __restrict__ rays, const float* __restrict__ dpl, int V, int D, int w,
                     int h, float cx, float cy, float sigma, float* __restrict__ cost, float* __restrict__ bv,
                     float* __restrict__ depth, float* __restrict__ conf) {
-  constexpr int GROUPS_PER_BLOCK = 256 / LANES;
-  __shared__ TapRec recs[256];
+  constexpr int GROUPS_PER_BLOCK = BT / LANES;
+  __shared__ TapRec recs[BT];
   // per-plane totals: thread t owns s_tot[b][t] (plane LANES b + lane of its pixel). Kept in shared memory so that the batch
   // loop can stay ROLLED: fully unrolled over the NB batches the kernel was instruction-fetch bound (ncu: 2.5 "no
   // instruction" stall cycles per issue with ~80 KB of code)
-  __shared__ float s_tot[NB][256];
+  __shared__ float s_tot[NB][BT];
   const int hw = w * h;
   const int lane = threadIdx.x % LANES;
   const int grp = threadIdx.x / LANES;
@@ -341,9 +341,12 @@ template <bool L1>
 int launch_sweep2(int G, int D, int hw, cudaStream_t st, const float4* ref_w, const float4* src_w, const float4* ref_n,
                   const float4* src_n, const float* t1, const float* KR, const float* rays, const float* dpl, int V, int w, int h, float cx,
                   float cy, float sigma, float* cost, float* bv, float* depth, float* conf) {
-#define NRGBD_SWEEP2(LN, P, NBV)                                                                                                   \
-  plane_sweep2_kernel<LN, P, L1, NBV><<<ceil_div((long long)hw * LN, 256), 256, 0, st>>>(ref_w, src_w, G, ref_n, src_n, t1, KR, rays, dpl, \
-                                                                                        V, D, w, h, cx, cy, sigma, cost, bv, depth, conf)
+#define NRGBD_SWEEP2_V(LN, P, NBV, BTV, MB)                                                                                          \
+  plane_sweep2_kernel<LN, P, L1, NBV, BTV, MB><<<ceil_div((long long)hw * LN, BTV), BTV, 0, st>>>(ref_w, src_w, G, ref_n, src_n, t1, KR, \
+                                                                                        rays, dpl, V, D, w, h, cx, cy, sigma, cost, bv, depth, conf)
+// 128-thread blocks with a 6-resident-block register target (80 registers, no spills): measured 232 us vs 241 us (256, 3)
+// and 277 us (256, 2) at 120x160x64x4x67; without the target ptxas takes 144 registers and the kernel runs at 419 us
+#define NRGBD_SWEEP2(LN, P, NBV) NRGBD_SWEEP2_V(LN, P, NBV, 128, 6)
   if (G == 16 && (long long)hw * D >= (8ll << 20)) {      // 64 wide channels, large volumes: 8 lanes x 2 slices (measured: -12 % at 270x480x256x8,
                                                            // +15 % at 120x160x64x4 where the lower occupancy costs more than the overhead saves)
     const int nb = (D + 7) / 8;
@@ -360,6 +363,7 @@ int launch_sweep2(int G, int D, int hw, cudaStream_t st, const float4* ref_w, co
     return NRGBD_ERR_UNSUPPORTED;
   }
 #undef NRGBD_SWEEP2
+#undef NRGBD_SWEEP2_V
   return NRGBD_OK;
 }
 

@@ -35,8 +35,9 @@ def timeit(fn, iters=20, warm=3):
 
 def main():
     h, w, C, V, D = 120, 160, 67, 4, 64
-    if len(sys.argv) > 1:
-        h, w, C, V, D = [int(x) for x in sys.argv[1:6]]
+    pos = [a for a in sys.argv[1:] if '=' not in a]
+    if pos:
+        h, w, C, V, D = [int(x) for x in pos[:5]]
     hw = h * w
     rng = np.random.RandomState(0)
     Cw, Cn = C - C % 4, C % 4
@@ -59,6 +60,9 @@ def main():
                                               ptr(K), ptr(R), ptr(t), ptr(rays), ptr(dpl), F(w / 2), F(h / 2), F(10.), 0,
                                               ptr(ws), ptr(cost), st()))
     res = {}
+    med, mn = timeit(sweep)
+            print(json.dumps(dict(shape=[h, w, C, V, D], sweep_variant=v, us_med=med, us_min=mn)), flush=True)
+        return
     med, mn = timeit(sweep)
     alg = (1 + V) * C * hw * 4 + D * hw * 4 + 3 * hw * 4
     res['sweep'] = dict(us_med=med, us_min=mn, alg_MB=alg / 1e6, GBps=alg / med / 1e3,
