@@ -60,10 +60,10 @@ CONFIGS = {
     'c2': dict(kind='first', H=480, W=640, D=64, V=4, r=2, intr=SCANNET, inflight=3,
                workload='scannet640x480_d64_v4_dnet_dpv_plus_rnet (BASELINE.json configs[1]; SURVEY C2)',
                metric='depth frames/sec at 640x480x64-plane x4-view'),
-    'c3': dict(kind='stream', H=480, W=640, D=64, V=4, r=2, intr=SCANNET, n_stream=30,
+    'c3': dict(kind='stream', H=480, W=640, D=64, V=4, r=2, intr=SCANNET, n_stream=30, inflight=2,
                workload='scannet640x480_d64_v4_full_kvnet_stream30 (BASELINE.json configs[2]; SURVEY C3)',
                metric='depth frames/sec at 640x480x64-plane x4-view, full KVNet (D-Net + K-Net + 2x R-Net + propagation), streaming'),
-    'c4': dict(kind='stream', H=376, W=1248, D=128, V=4, r=2, intr=dict(fx=721.5377, fy=721.5377, cx=624.0, cy=188.0, d=(1.0, 60.0)), n_stream=12,
+    'c4': dict(kind='stream', H=376, W=1248, D=128, V=4, r=2, intr=dict(fx=721.5377, fy=721.5377, cx=624.0, cy=188.0, d=(1.0, 60.0)), n_stream=12, inflight=2,
                workload='kitti1248x376_d128_v4_full_kvnet_stream (BASELINE.json configs[3]; 1242x375 is rejected by the reference CNN; SURVEY C4)',
                metric='depth frames/sec at 1248x376x128-plane x4-view, full KVNet, streaming'),
     'c5': dict(kind='first', H=1080, W=1920, D=256, V=8, r=4, intr=dict(fx=1755.0, fy=1755.0, cx=960.0, cy=540.0, d=(0.1, 5.0)), inflight=1,
@@ -569,42 +569,67 @@ def run_engine(args, cfg):
     else:
         # ------------------------------------------------------------------ streaming full KVNet (c3, c4)
         n_stream = cfg['n_stream']
-        frames, exts = make_video(cfg, n_stream + 2 * R_WIN, seed=7 + rank)      # every rank streams its own trajectory chunk
-        dev_f = [torch.from_numpy(f[None]).to(dev) for f in frames]
-        u8 = [np.ascontiguousarray(np.clip((f.transpose(1, 2, 0) * 0.226 + 0.45) * 255.0, 0, 255).astype(np.uint8)) for f in frames]
-        pin_u8 = [torch.from_numpy(a).pin_memory() for a in u8]
-        win_list, pose_list, next_list = [], [], []
-        for i in range(n_stream):
-            poses, idx = synth.window_rel_poses(exts, R_WIN + i, R_WIN)
-            win_list.append(torch.cat([dev_f[j] for j in idx] + [dev_f[R_WIN + i]], 0).contiguous())
-            pose_list.append(torch.from_numpy(np.ascontiguousarray(poses, np.float32)).to(dev))
-            next_list.append(torch.from_numpy(np.linalg.inv(poses[R_WIN].astype(np.float64)).astype(np.float32)).to(dev))     # inverse of the (t+1) pose
+        # `inflight` independent trajectory chunks stream concurrently on their own engines / CUDA streams (the same chunks
+        # sharding.chunk_trajectory hands to different ranks at N > 1): one chunk's HBM-bound BatchNorm passes overlap the other's
+        # tensor-bound K-Net convolutions. Every chunk keeps its own sequential recursion.
+        inflight = max(1, args.inflight if args.inflight > 0 else cfg.get('inflight', 1))
+        models = [model]
+        for _ in range(inflight - 1):
+            m2 = new_model()
+            m2.load_state_dict(model.state_dict())
+            m2 = m2.to(dev); m2.conv_math = args.conv_math
+            models.append(m2)
+        streams = [torch.cuda.current_stream()] + [torch.cuda.Stream(device=dev) for _ in range(inflight - 1)]
+        trajs = []
+        for t in range(inflight):
+            frames, exts = make_video(cfg, n_stream + 2 * R_WIN, seed=7 + rank + 1000 * t)   # every rank / chunk streams its own trajectory
+            dev_f = [torch.from_numpy(f[None]).to(dev) for f in frames]
+            u8 = [np.ascontiguousarray(np.clip((f.transpose(1, 2, 0) * 0.226 + 0.45) * 255.0, 0, 255).astype(np.uint8)) for f in frames]
+            tr = dict(exts=exts, pin_u8=[torch.from_numpy(a).pin_memory() for a in u8], win=[], pose=[], nxt=[])
+            for i in range(n_stream):
+                poses, idx = synth.window_rel_poses(exts, R_WIN + i, R_WIN)
+                tr['win'].append(torch.cat([dev_f[j] for j in idx] + [dev_f[R_WIN + i]], 0).contiguous())
+                tr['pose'].append(torch.from_numpy(np.ascontiguousarray(poses, np.float32)).to(dev))
+                tr['nxt'].append(torch.from_numpy(np.linalg.inv(poses[R_WIN].astype(np.float64)).astype(np.float32)).to(dev))   # inverse of the (t+1) pose
+            with torch.cuda.stream(streams[t]), torch.no_grad():
+                models[t](tr['win'][0][-1:], tr['win'][0][None, :-1], tr['pose'][0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
+            ent = models[t]._engine(H_IMG, W_IMG, V_SRC, dev)
+            models[t]._set_camera(ent, 1, cam=cam)         # per-call intrinsics (K-Net image warp, propagation): the same camera here
+            tr['h'] = ent['h']
+            tr['o_ref'] = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
+            tr['o_cur'] = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
+            tr['o_dpv'] = torch.empty((D_PLANES, h, w), device=dev)
+            tr['o_dep'] = torch.empty((h, w), device=dev)
+            tr['priors'] = [torch.empty((D_PLANES, h, w), device=dev) for _ in range(2)]
+            trajs.append(tr)
+        torch.cuda.synchronize()
+        pin_u8, exts = trajs[0]['pin_u8'], trajs[0]['exts']
         h2d_bytes = pin_u8[0].numel() + V_SRC * 64
         d2h_bytes = 2 * H_IMG * W_IMG * 4
-        with torch.no_grad():
-            model(win_list[0][-1:], win_list[0][None, :-1], pose_list[0][None], torch.zeros(1), cam_intrinsics=[cam], BV_predict=None)
-        ent = model._engine(H_IMG, W_IMG, V_SRC, dev)
-        model._set_camera(ent, 1, cam=cam)             # per-call intrinsics (K-Net image warp, propagation): the same camera here
-        hnd = ent['h']
-        stream = torch.cuda.current_stream()
-        st_ptr = ctypes.c_void_p(stream.cuda_stream)
-        o_ref = torch.empty((D_PLANES, H_IMG, W_IMG), device=dev)
-        o_dpv = torch.empty((D_PLANES, h, w), device=dev)
-        o_dep = torch.empty((h, w), device=dev)
-        priors = [torch.empty((D_PLANES, h, w), device=dev) for _ in range(2)]
+        hnd = trajs[0]['h']
+        stream = streams[0]
 
         def stream_step(i, have_prior):
-            """One depth frame of the stream on resident inputs: forward (K-Net when a prior exists) + propagation."""
-            k = i % n_stream
-            flush.zero_()
-            if k == 0 or not have_prior:
-                check(L.nrgbd_kvnet_forward(hnd, ptr(win_list[k]), ptr(pose_list[k]), None, ptr(o_ref), None, None, None, ptr(o_dep), None, st_ptr))
-            else:
-                check(L.nrgbd_kvnet_forward(hnd, ptr(win_list[k]), ptr(pose_list[k]), ptr(priors[i % 2]), None, ptr(o_ref), None, ptr(o_dpv),
-                                            ptr(o_dep), None, st_ptr))
-            check(L.nrgbd_kvnet_propagate(hnd, None, ptr(next_list[k]), ptr(priors[(i + 1) % 2]), st_ptr))
-        stream_step(0, False)
-        for i in range(1, 3 + Wm):                     # warm-up: first window + steady-state graph capture
+            """One depth frame of one chunk's stream on resident inputs: forward (K-Net when a prior exists) + propagation."""
+            t = i % inflight
+            j = i // inflight
+            k = j % n_stream
+            tr = trajs[t]
+            sp = ctypes.c_void_p(streams[t].cuda_stream)
+            with torch.cuda.stream(streams[t]):
+                if t == 0:
+                    flush.zero_()
+                if k == 0 or not have_prior:
+                    check(L.nrgbd_kvnet_forward(tr['h'], ptr(tr['win'][k]), ptr(tr['pose'][k]), None, ptr(tr['o_ref']), None, None, None,
+                                                ptr(tr['o_dep']), None, sp))
+                else:
+                    # both refined maps, like models/KVNET.py:93-185 returns them (R-Net runs on BV_cur AND on the K-Net DPV)
+                    check(L.nrgbd_kvnet_forward(tr['h'], ptr(tr['win'][k]), ptr(tr['pose'][k]), ptr(tr['priors'][j % 2]), ptr(tr['o_cur']), ptr(tr['o_ref']),
+                                                None, ptr(tr['o_dpv']), ptr(tr['o_dep']), None, sp))
+                check(L.nrgbd_kvnet_propagate(tr['h'], None, ptr(tr['nxt'][k]), ptr(tr['priors'][(j + 1) % 2]), sp))
+        for i in range(inflight):
+            stream_step(i, False)
+        for i in range(inflight, (3 + Wm) * inflight):     # warm-up: first window + steady-state graph capture
             stream_step(i, True)
         torch.cuda.synchronize()
         if rank == 0:
@@ -613,16 +638,20 @@ def run_engine(args, cfg):
         L.nrgbd_reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        base = 3 + Wm
+        for s_ in streams[1:]:
+            s_.wait_stream(stream)
+        base = (3 + Wm) * inflight
         for i in range(K):
             stream_step(base + i, True)                # a 30-frame window: the recursion restarts (first-window frame) every n_stream frames
+        for s_ in streams[1:]:
+            stream.wait_stream(s_)
         e1.record(stream)
         barrier()
         launches = int(L.nrgbd_launch_count())
         ms_value = max_ms(e0.elapsed_time(e1), world, dev)
 
         def eager_frame(i):
-            stream_step(1 + i % (n_stream - 1), True)
+            stream_step((1 + i % (n_stream - 1)) * inflight, True)      # chunk 0, a steady-state frame
 
     # ---------------- roofline pass: per-kernel CUDA events, eager, ONE frame in flight, right after the timed region -----------
     P_PROF = 4 if H_IMG * W_IMG * D_PLANES <= 1248 * 376 * 128 else 2
@@ -700,40 +729,59 @@ def run_engine(args, cfg):
         barrier()
         host_depth = h_depth[0]
     else:
-        # the reference's streaming loop (test_KVNet.py:190-250) on the mirrors: one new decoded frame per step
-        fw = m_preprocess.FrameWindow(t_win_r=R_WIN, img_size=None, device=dev)
-        h_depth = torch.empty((H_IMG, W_IMG)).pin_memory()
-        h_conf = torch.empty((H_IMG, W_IMG)).pin_memory()
-        state = {'bv': None, 'pos': 0}
+        # the reference's streaming loop (test_KVNet.py:190-250) on the mirrors: one new decoded frame per step and chunk
+        fws = [m_preprocess.FrameWindow(t_win_r=R_WIN, img_size=None, device=dev) for _ in range(inflight)]
+        h_depths = [torch.empty((H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
+        h_confs = [torch.empty((H_IMG, W_IMG)).pin_memory() for _ in range(inflight)]
+        states = [{'bv': None, 'pos': 0, 'ev': None} for _ in range(inflight)]
 
-        def step_e2e():
-            flush.zero_()
-            if state['pos'] == 0 or state['pos'] >= len(pin_u8):          # new trajectory chunk: refill the window, restart the recursion
-                fw.frames.clear(); state['bv'] = None
-                for j in range(2 * R_WIN):
-                    fw.push(pin_u8[j], exts[j])
-                state['pos'] = 2 * R_WIN
-            k = state['pos']; state['pos'] += 1
-            fw.push(pin_u8[k], exts[k])                    # H2D: ONE decoded uint8 frame; the other 2r frames of the window are resident
-            fds = fw.frame_dicts()
-            ref_d, src_d = fds[R_WIN], [fd for j, fd in enumerate(fds) if j != R_WIN]
-            inv_ref = np.linalg.inv(ref_d['extM'])
-            poses = np.stack([fd['extM'].dot(inv_ref) for fd in src_d]).astype(np.float32)      # warping.homography.get_rel_extrinsicM
-            poses_t = torch.from_numpy(poses[None]).to(dev, non_blocking=True)
-            dmap, bv = step_mod.test(model, d, [cam], R_WIN, [ref_d], [src_d], poses_t, state['bv'], R_net=True)
-            maps = export_res.depth_conf_maps(dmap, d, want_float=True, want_u16=False)
-            h_depth.copy_(maps['dmap'], non_blocking=True)
-            h_conf.copy_(maps['conf'], non_blocking=True)
-            torch.cuda.current_stream().synchronize()      # the user reads the maps on the host before the next frame arrives
-            state['bv'] = bv
-        for i in range(3 + Wm):
-            step_e2e()
+        def consume(t):
+            if states[t]['ev'] is not None:
+                states[t]['ev'].synchronize()          # the user reads this chunk's maps on the host before its next frame arrives
+                states[t]['ev'] = None
+
+        def step_e2e(i):
+            t = i % inflight
+            consume(t)
+            state, fw, tr = states[t], fws[t], trajs[t]
+            with torch.cuda.stream(streams[t]):
+                if t == 0:
+                    flush.zero_()
+                if state['pos'] == 0 or state['pos'] >= len(tr['pin_u8']):      # new trajectory chunk: refill the window, restart the recursion
+                    fw.frames.clear(); state['bv'] = None
+                    for j in range(2 * R_WIN):
+                        fw.push(tr['pin_u8'][j], tr['exts'][j])
+                    state['pos'] = 2 * R_WIN
+                k = state['pos']; state['pos'] += 1
+                fw.push(tr['pin_u8'][k], tr['exts'][k])       # H2D: ONE decoded uint8 frame; the other 2r frames of the window are resident
+                fds = fw.frame_dicts()
+                ref_d, src_d = fds[R_WIN], [fd for j, fd in enumerate(fds) if j != R_WIN]
+                inv_ref = np.linalg.inv(ref_d['extM'])
+                poses = np.stack([fd['extM'].dot(inv_ref) for fd in src_d]).astype(np.float32)      # warping.homography.get_rel_extrinsicM
+                poses_t = torch.from_numpy(poses[None]).to(dev, non_blocking=True)
+                dmap, bv = step_mod.test(models[t], d, [cam], R_WIN, [ref_d], [src_d], poses_t, state['bv'], R_net=True)
+                maps = export_res.depth_conf_maps(dmap, d, want_float=True, want_u16=False)
+                h_depths[t].copy_(maps['dmap'], non_blocking=True)
+                h_confs[t].copy_(maps['conf'], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(streams[t]); state['ev'] = ev
+                state['bv'] = bv
+        for i in range((3 + Wm) * inflight):
+            step_e2e(i)
+        for t in range(inflight):
+            consume(t)
         barrier()
         e0.record(stream)
+        for s_ in streams[1:]:
+            s_.wait_stream(stream)
         for i in range(K):
-            step_e2e()
+            step_e2e((3 + Wm) * inflight + i)
+        for t in range(inflight):
+            consume(t)
+        for s_ in streams[1:]:
+            stream.wait_stream(s_)
         e1.record(stream)
         barrier()
+        h_depth = h_depths[0]
         host_depth = h_depth
     e2e_value = world * K / (max_ms(e0.elapsed_time(e1), world, dev) * 1e-3)
     sampler.stop = True
@@ -755,6 +803,7 @@ def run_engine(args, cfg):
                        'parallelism': 'dp%d (%s sharded, weights NCCL-broadcast once)' % (world, 'trajectory chunks' if stream_mode else 'frames'),
                        'l2': 'explicit 256 MiB flush write before every %s step (inside the timed region)' % ('' if inflight == 1 else '%d-th' % inflight),
                        'frames_in_flight': inflight,
+                       'in_flight_unit': 'independent trajectory chunks, each with its own sequential recursion' if stream_mode else 'independent first-window frames',
                        'weights': 'random init of the reference architecture (arch.synth_state_dict seed 5)',
                        'hbm_kernels': {'plane_sweep': {'avg_us': 1e3 * sw_ms / max(sw_n, 1), 'algorithmic_GBps': sweep_gbs, 'frac_of_hbm_peak': sweep_gbs / peaks['hbm_gbs'],
                                                        'note': 'fused plane-sweep (+ log-softmax) kernel; at C = 67 it is gather / FFMA bound, not HBM bound (SURVEY 8d)'}},
@@ -794,7 +843,7 @@ def main():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layer-table', default=None, help='write the per-shape conv table of the roofline pass to this JSON file')
-    ap.add_argument('--inflight', type=int, default=0, help='independent frames in flight on separate streams (first-window configs; 0 = the config default)')
+    ap.add_argument('--inflight', type=int, default=0, help='independent frames (first-window configs) or trajectory chunks (streaming configs) in flight on separate CUDA streams; 0 = the config default')
     ap.add_argument('--dev-bn-unroll', type=int, default=0, help='development: vectors in flight per thread in the BatchNorm pass')
     ap.add_argument('--dev-smem-cap-kb', type=int, default=0, help='development: cap conv_h2 shared memory (co-residency experiment)')
     ap.add_argument('--conv-math', default='f16x3', choices=['fp32', 'tf32x3', 'f16x3'],

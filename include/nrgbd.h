@@ -218,6 +218,13 @@ int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const
                               float eps, float* run_mean, float* run_var, float momentum, const float* res, int relu,
                               long long n_pos, int Cs, int C, float* y, void* y_hi, void* y_lo,
                               unsigned int* rezero_counter, nrgbd_stream_t stream);
+/* Second half of a SINGLE-output-channel k3 convolution (models/basic.py:136-137, K-Net's Conv3d(64 -> 1)): with
+ * Q[n][d][h][w][t] = sum_c x[..][c] w[0][c][t] - one pointwise convolution with kd*k*k output channels, e.g. nrgbd_conv_nhwc_h2 on
+ * the weight packed with transposed = 1, Cout = kd*k*k, taps = 1 - this gathers
+ * out[n][d][h][w] = bias + sum_t Q[n][d + tz - kd/2][h + ty - 1][w + tx - 1][t]  (zero outside the volume; t = (tz*3 + ty)*3 + tx).
+ * Q has Cs >= kd*k*k floats per position; k = 3, kd in {1, 3}. */
+int nrgbd_tap_gather_sum(const float* Q, int N, int D, int H, int W, int Cs, int kd, int k, float bias, float* out,
+                         nrgbd_stream_t stream);
 /* y = [relu](x*scale + shift) [+ res] over n_pos positions of Cs channels (C logical). */
 int nrgbd_bn_apply(const float* x, const float* scale, const float* shift, const float* res, int relu,
                    long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);

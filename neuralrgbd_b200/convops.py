@@ -310,6 +310,30 @@ def conv_h2(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stat
     return (out, stats) if want_stats else out
 
 
+def conv_cout1_h2(x, w, bias=0.0):
+    """Single-output-channel k3 convolution (K-Net's last layer, models/basic.py:136-137) the way the engine runs it:
+    a pointwise f16-pair conv to one channel per tap + nrgbd_tap_gather_sum. x [N, C, D, H, W] (or [N, C, H, W]),
+    w [1, C, 3, 3, 3] (or [1, C, 3, 3]) -> [N, 1, D, H, W] ([N, 1, H, W])."""
+    L = _lib.lib()
+    is3d = x.dim() == 5
+    N = x.shape[0]
+    D = x.shape[2] if is3d else 1
+    H, W = x.shape[-2], x.shape[-1]
+    Cin = w.shape[1]
+    kd = w.shape[2] if is3d else 1
+    taps = kd * 9
+    wt = w[0].reshape(Cin, taps, 1, 1)                  # [Cin][Cout' = taps][1][1]: the transposed-kind source layout
+    wp, Cin_pad, Cout_pad, BN = pack_weight_h2(wt, transposed=True)
+    xh, xl = split_f16_pair(to_cl_padded(x, Cin_pad))
+    Cs = pad4(taps)
+    q = torch.empty((N, D, H, W, Cs), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_conv_nhwc_h2(ptr(xh), ptr(xl), N, D, H, W, Cin_pad, Cin_pad, ptr(wp), None, taps, Cout_pad, BN, 1, 1, 1, 1, 0, 1,
+                               ptr(q), H, W, Cs, 0, 0, None, _st()))
+    out = torch.empty((N, 1) + ((D,) if is3d else ()) + (H, W), device=x.device, dtype=torch.float32)
+    check(L.nrgbd_tap_gather_sum(ptr(q), N, D, H, W, Cs, kd, 3, ctypes.c_float(bias), ptr(out), _st()))
+    return out
+
+
 def conv_transpose2d_h2(x, w, bias=None, leaky=False):
     L = _lib.lib()
     N, Cin, Hin, Win = x.shape

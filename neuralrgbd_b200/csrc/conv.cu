@@ -366,6 +366,44 @@ bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ st
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-output-channel 3x3x3 convolution as (1x1x1 conv to one channel PER TAP) + (shifted sum of the taps).
+// K-Net's last layer (models/basic.py:136-137, Conv3d(64 -> 1, k3)) has Cout = 1: as an implicit GEMM its N is 1 (padded to
+// 16), i.e. 27 x 4 x 3 tiny MMAs per 128 positions - issue-bound at 8 TFLOP/s. Re-associated,
+//   out[p] = sum_t sum_c x[p + off_t][c] w[t][c] = sum_t Q[p + off_t][t],   Q[q][t] = sum_c x[q][c] w[t][c],
+// Q is ONE pointwise convolution with 27 output channels (a single N = 32 GEMM on the tensor cores, 27x fewer MMAs) and the
+// rest is this gather: every Q element is used exactly once.
+// Q: [N][D][H][W][Cs] fp32 (Cs >= kd*k*k), out: [N][D][H][W] fp32, zero padding `pad` in all three axes.
+// ---------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+tap_gather_sum_kernel(const float* __restrict__ Q, int D, int H, int W, int Cs, int kd, float bias, float* __restrict__ out) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int nd = blockIdx.z;                       // n * D + d
+  const int d = nd % D;
+  if (x >= W || y >= H) return;
+  const int pd = kd / 2, p = K / 2;
+  float acc = bias;
+  for (int tz = 0; tz < kd; ++tz) {
+    const int dz = d + tz - pd;
+    if (dz < 0 || dz >= D) continue;
+    const float* plane = Q + (size_t)(nd + tz - pd) * H * W * Cs;
+#pragma unroll
+    for (int ty = 0; ty < K; ++ty) {
+      const int yy = y + ty - p;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int tx = 0; tx < K; ++tx) {
+        const int xx = x + tx - p;
+        if (xx < 0 || xx >= W) continue;
+        acc += __ldg(plane + ((size_t)yy * W + xx) * Cs + (tz * K + ty) * K + tx);
+      }
+    }
+  }
+  out[((size_t)nd * H + y) * W + x] = acc;
+}
+
 int g_bn_unroll = 1;      // vectors in flight per thread in the BatchNorm pass (development knob, nrgbd_dev_set_bn_unroll)
 
 }  // namespace
@@ -526,6 +564,19 @@ int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const
     bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
                                                               n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
                                                               rezero_counter ? stats : nullptr, rezero_counter);
+  NRGBD_COUNT(1);
+  NRGBD_LAUNCH_CHECK();
+  return NRGBD_OK;
+}
+
+// out[n][d][h][w] = bias + sum over the kd x k x k taps t of Q[n][d + tz - kd/2][h + ty - k/2][w + tx - k/2][t] (zero outside):
+// the second half of a single-output-channel convolution whose first half is the pointwise convolution Q = x * w[t][:]
+// (see tap_gather_sum_kernel). k = 3, kd in {1, 3}.
+int nrgbd_tap_gather_sum(const float* Q, int N, int D, int H, int W, int Cs, int kd, int k, float bias, float* out, cudaStream_t st) {
+  NRGBD_REQUIRE(Q && out && N > 0 && D > 0 && H > 0 && W > 0 && k == 3 && (kd == 1 || kd == 3) && Cs >= kd * k * k, "bad arguments");
+  NRGBD_REQUIRE((long long)N * D <= 65535, "too many planes for one launch");
+  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), N * D);
+  tap_gather_sum_kernel<3><<<grid, 256, 0, st>>>(Q, D, H, W, Cs, kd, bias, out);
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;

@@ -258,6 +258,29 @@ const PackedH2* packw_h2(Eng* e, const std::string& name, int Cout, int Cin, int
   return &e->packed_h2[name];
 }
 
+// Weight of a single-output-channel conv [1][Cin][taps] packed as the POINTWISE conv [taps][Cin] (one output channel per tap) for
+// the tap-gather form of K-Net's last layer (nrgbd_tap_gather_sum): that is the transposed-kind packing with Cout = taps.
+const PackedH2* packw_h2_taps(Eng* e, const std::string& name, int Cin, int taps) {
+  const std::string key = name + "#taps";
+  auto it = e->packed_h2.find(key);
+  if (it != e->packed_h2.end()) return &it->second;
+  float* src = param(e, name);
+  if (!src) return nullptr;
+  auto pr = e->params[name];
+  if (pr.n != (long long)Cin * taps) {
+    if (e->rc == 0) { nrgbd_set_error("engine: parameter '%s' has %lld elements, expected %lld", name.c_str(), pr.n, (long long)Cin * taps); e->rc = NRGBD_ERR_BAD_ARG; }
+    return nullptr;
+  }
+  PackedH2 pk; pk.taps = 1;
+  nrgbd_conv_h2_plan(Cin, taps, &pk.Cin_pad, &pk.Cout_pad, &pk.BN);
+  void* q = nullptr;
+  if (cudaMalloc(&q, (size_t)2 * pk.Cin_pad * pk.Cout_pad * 2) != cudaSuccess) { e->rc = NRGBD_ERR_NOMEM; nrgbd_set_error("engine: cudaMalloc failed for packed weight"); return nullptr; }
+  pk.w = q;
+  ENG_CALL(e, nrgbd_pack_conv_weight_h2(src, 1, taps, Cin, 1, pk.Cin_pad, pk.Cout_pad, pk.w, (nrgbd_stream_t)e->st));
+  e->packed_h2[key] = pk;
+  return &e->packed_h2[key];
+}
+
 // f16-pair tensor path: any conv with >= 16 input channels whose activation carries the 32-channel padding
 bool use_h2(Eng* e, const Act& x) {
   return e->conv_math == 2 && x.C >= 16 && pad32(x.C) <= x.Cs && x.Cs % 8 == 0;
@@ -607,7 +630,30 @@ Act kv_net(Eng* e, const Act& vol) {
     c = o;
   }
   Act o = cb(c, "kv_net.classify.0", true, nullptr, 2); release(e, c);
-  Act gain = conv(e, o, "kv_net.classify.2.weight", 1, 3, 3, 1, 1, 1, nullptr, false, false, nullptr, 0, 1);
+  Act gain;
+  if (use_h2(e, o)) {
+    // Conv3d(f -> 1, k3) (models/basic.py:136-137) as a pointwise conv to 27 per-tap channels on the tensor cores + the shifted
+    // sum of the taps: as a direct implicit GEMM its N is 1 (27 x 12 sixteen-column MMAs per 128 positions, issue-bound)
+    const PackedH2* ph = packw_h2_taps(e, "kv_net.classify.2.weight", o.C, 27);
+    const PairBuf* pb = pair_of(e, o);
+    Act q; q.N = o.N; q.D = o.D; q.H = o.H; q.W = o.W; q.C = 27; q.Cs = 28; q.p = nullptr;
+    gain = acquire(e, o.N, o.D, o.H, o.W, 1, 1);
+    if (!e->rc) {
+      q.p = e->pool.acquire((size_t)q.floats() * sizeof(float));      // pad channel 27 is never read: no memset
+      if (!q.p) { nrgbd_set_error("engine: out of device memory (%lld floats)", q.floats()); e->rc = NRGBD_ERR_NOMEM; }
+    }
+    if (!e->rc) {
+      char tag[56];
+      snprintf(tag, sizeof(tag), "conv3d k3 s1 d1 %d->1 %dx%dx%dx%d", o.C, o.N, o.D, o.H, o.W);
+      ProfScope ps(e, 0, 2.0 * (double)o.pos() * o.C * 27, tag);
+      ENG_CALL(e, nrgbd_conv_nhwc_h2(pb->hi, pb->lo, o.N, o.D, o.H, o.W, ph->Cin_pad, o.Cs, ph->w, nullptr, 27, ph->Cout_pad, ph->BN, 1, 1, 1, 1,
+                                     0, 1, q.p, o.H, o.W, q.Cs, 0, 0, nullptr, (nrgbd_stream_t)e->st));
+      ENG_CALL(e, nrgbd_tap_gather_sum(q.p, o.N, o.D, o.H, o.W, q.Cs, 3, 3, 0.f, gain.p, (nrgbd_stream_t)e->st));
+    }
+    if (q.p) e->pool.release(q.p);
+  } else {
+    gain = conv(e, o, "kv_net.classify.2.weight", 1, 3, 3, 1, 1, 1, nullptr, false, false, nullptr, 0, 1);
+  }
   release(e, o);
   return gain;
 }

@@ -81,6 +81,24 @@ def test_conv3d_h2_vs_oracle():
         assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
 
 
+def test_conv3d_single_output_channel_tap_gather_vs_oracle():
+    """K-Net's last layer (Conv3d(f -> 1, k3), models/basic.py:136-137) in the form the engine runs it: a pointwise conv to one
+    channel per tap on the tensor cores + the shifted sum of the taps. Ragged extents exercise every border case of the gather."""
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(12)
+    for cin, shape in ((64, (9, 14, 18)), (28, (5, 33, 41)), (64, (3, 8, 32)), (64, (1, 9, 37))):
+        x = rng.standard_normal((1, cin) + shape).astype(np.float32)
+        w = (rng.standard_normal((1, cin, 3, 3, 3)) / math.sqrt(cin * 27)).astype(np.float32)
+        y = convops.conv_cout1_h2(T(x), T(w))
+        ref = N.conv3d(x, w)
+        assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
+    x = rng.standard_normal((2, 32, 17, 45)).astype(np.float32)          # 2-D form, batch of two
+    w = (rng.standard_normal((1, 32, 3, 3)) / math.sqrt(32 * 9)).astype(np.float32)
+    y = convops.conv_cout1_h2(T(x), T(w), bias=0.25)
+    ref = N.conv2d(x, w, np.array([0.25], np.float32), 1, 1, 1)
+    assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
+
+
 def test_conv_transpose2d_h2_vs_oracle():
     from neuralrgbd_b200 import convops
     rng = np.random.RandomState(3)
