@@ -211,12 +211,14 @@ int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, cons
                          float eps, float* run_mean, float* run_var, float momentum, const float* res, int relu,
                          long long n_pos, int Cs, int C, float* y, nrgbd_stream_t stream);
 /* same pass, also (or only: y may be NULL) emitting the result as the split-fp16 operand pair (y_hi, y_lo: half tensors with
- * x's layout; both may be NULL) of the f16-pair convolution that consumes it - see nrgbd_conv_nhwc_h2. rezero_counter
+ * x's layout; both may be NULL) of the f16-pair convolution that consumes it - see nrgbd_conv_nhwc_h2. The residual is either
+ * the fp32 tensor `res` or the operand pair (res_hi, res_lo) of a tensor that was only ever written as a pair (its value
+ * hi + lo * 2^-11 carries 22 significand bits); at most one of the two forms. rezero_counter
  * (optional, a zero-initialised device word): the last block to have read `stats` sets them back to zero, so the next
  * convolution accumulates into a clean buffer without a memset in between. */
 int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const float* gamma, const float* beta,
-                              float eps, float* run_mean, float* run_var, float momentum, const float* res, int relu,
-                              long long n_pos, int Cs, int C, float* y, void* y_hi, void* y_lo,
+                              float eps, float* run_mean, float* run_var, float momentum, const float* res, const void* res_hi,
+                              const void* res_lo, int relu, long long n_pos, int Cs, int C, float* y, void* y_hi, void* y_lo,
                               unsigned int* rezero_counter, nrgbd_stream_t stream);
 /* Second half of a SINGLE-output-channel k3 convolution (models/basic.py:136-137, K-Net's Conv3d(64 -> 1)): with
  * Q[n][d][h][w][t] = sum_c x[..][c] w[0][c][t] - one pointwise convolution with kd*k*k output channels, e.g. nrgbd_conv_nhwc_h2 on

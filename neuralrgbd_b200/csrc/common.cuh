@@ -116,6 +116,16 @@ __device__ __forceinline__ void nrgbd_split_pair(float a, __half& hi, __half& lo
   const float r = (c - __half2float(hi)) * 2048.f;           // exact difference, exact power-of-two scale
   lo = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
 }
+// value of four packed pairs: hi + lo * 2^-11 (exact in fp32 when |lo| * 2^-11 <= ulp(hi) / 2, i.e. always for pairs made by nrgbd_split_pair)
+__device__ __forceinline__ void nrgbd_join_pair4(const uint2& hi, const uint2& lo, float* o) {
+  const uint32_t hw[2] = {hi.x, hi.y}, lw[2] = {lo.x, lo.y};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float h = __half2float(__ushort_as_half((unsigned short)(hw[k >> 1] >> (16 * (k & 1)))));
+    const float l = __half2float(__ushort_as_half((unsigned short)(lw[k >> 1] >> (16 * (k & 1)))));
+    o[k] = fmaf(l, 1.f / 2048.f, h);
+  }
+}
 __device__ __forceinline__ void nrgbd_split_pair4(const float* o, uint2& hi, uint2& lo) {
   __half h[4], l[4];
 #pragma unroll

@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(256)
 bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ stats, double count,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                       float* __restrict__ run_mean, float* __restrict__ run_var, float momentum,
-                      const float* __restrict__ res, int relu, long long n4, int Cs, int C, float* __restrict__ y,
+                      const float* __restrict__ res, const uint2* __restrict__ res_hi, const uint2* __restrict__ res_lo, int relu,
+                      long long n4, int Cs, int C, float* __restrict__ y,
                       uint2* __restrict__ y_hi, uint2* __restrict__ y_lo, double* __restrict__ stats_to_zero,
                       unsigned int* __restrict__ done_counter) {
   __shared__ float s_scale[512], s_shift[512];
@@ -337,6 +338,11 @@ bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ st
       if (i < n4) {
         v[u] = reinterpret_cast<const float4*>(x)[i];
         if (res) rr[u] = reinterpret_cast<const float4*>(res)[i];
+        else if (res_hi) {               // the residual as the operand pair its producer emitted (no fp32 copy of it exists)
+          float q[4];
+          nrgbd_join_pair4(res_hi[i], res_lo[i], q);
+          rr[u] = make_float4(q[0], q[1], q[2], q[3]);
+        }
       }
     }
 #pragma unroll
@@ -355,7 +361,7 @@ bn_apply_stats_kernel(const float* __restrict__ x, const double* __restrict__ st
           o[k] = 0.f;
         }
       }
-      if (res) { o[0] += rr[u].x; o[1] += rr[u].y; o[2] += rr[u].z; o[3] += rr[u].w; }
+      if (res || res_hi) { o[0] += rr[u].x; o[1] += rr[u].y; o[2] += rr[u].z; o[3] += rr[u].w; }
       if (y) reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
       if (y_hi) {                      // the consumer is an f16-pair convolution: emit its operand planes in the same pass
         uint2 h, l;
@@ -533,8 +539,8 @@ int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, cons
   long long n4 = n_pos * Cs / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                            n4, Cs, C, y, nullptr, nullptr, nullptr, nullptr);
+  bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, nullptr,
+                                                            nullptr, relu, n4, Cs, C, y, nullptr, nullptr, nullptr, nullptr);
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();
   return NRGBD_OK;
@@ -545,24 +551,28 @@ int nrgbd_bn_apply_stats(const float* x, const double* stats, double count, cons
 // rezero_counter (optional): a zero-initialised device word; when given, the last block to have read `stats` sets them back
 // to zero (and the word back to 0), so the next convolution can accumulate into `stats` without a memset in between.
 int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const float* gamma, const float* beta, float eps,
-                              float* run_mean, float* run_var, float momentum, const float* res, int relu, long long n_pos, int Cs,
-                              int C, float* y, void* y_hi, void* y_lo, unsigned int* rezero_counter, cudaStream_t st) {
+                              float* run_mean, float* run_var, float momentum, const float* res, const void* res_hi, const void* res_lo,
+                              int relu, long long n_pos, int Cs, int C, float* y, void* y_hi, void* y_lo, unsigned int* rezero_counter,
+                              cudaStream_t st) {
   NRGBD_REQUIRE(x && stats && gamma && beta && (y || (y_hi && y_lo)) && (y_hi == nullptr) == (y_lo == nullptr) && Cs % 4 == 0 && C <= Cs &&
                     C <= 512 && n_pos > 0 && count > 0, "bad arguments");
+  NRGBD_REQUIRE((res_hi == nullptr) == (res_lo == nullptr) && !(res && res_hi), "the residual is either an fp32 tensor or an operand pair");
+  const uint2* rh = reinterpret_cast<const uint2*>(res_hi);
+  const uint2* rl = reinterpret_cast<const uint2*>(res_lo);
   long long n4 = n_pos * Cs / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (g_bn_unroll == 4)
-    bn_apply_stats_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                              n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
+    bn_apply_stats_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, rh, rl,
+                                                              relu, n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
                                                               rezero_counter ? stats : nullptr, rezero_counter);
   else if (g_bn_unroll == 2)
-    bn_apply_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                              n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
+    bn_apply_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, rh, rl,
+                                                              relu, n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
                                                               rezero_counter ? stats : nullptr, rezero_counter);
   else
-    bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, relu,
-                                                              n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
+    bn_apply_stats_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, rh, rl,
+                                                              relu, n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
                                                               rezero_counter ? stats : nullptr, rezero_counter);
   NRGBD_COUNT(1);
   NRGBD_LAUNCH_CHECK();

@@ -24,6 +24,7 @@ namespace {
 struct Act {            // channels-last activation [N][D][H][W][Cs]
   float* p = nullptr;
   int N = 0, D = 1, H = 0, W = 0, C = 0, Cs = 0;
+  bool pair_only = false;   // f16-pair mode: the BatchNorm pass wrote only the operand pair; p holds the RAW conv output (and keys the pair)
   long long pos() const { return (long long)N * D * H * W; }
   long long floats() const { return pos() * Cs; }
 };
@@ -363,7 +364,8 @@ Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k
 // `pre` is the Sequential(Conv, BN) prefix: weights pre.0.weight, pre.1.{weight,bias,running_*}.
 // out_use (f16-pair mode only): 0 = the result is read as fp32 only; 1 = also by a convolution (the BatchNorm pass emits the
 // split-fp16 operand planes together with the fp32 tensor); 2 = ONLY by a convolution (no fp32 copy is written: y.p keeps
-// the raw conv output and must not be read as an activation).
+// the raw conv output and must not be read as an activation). A residual `res` that itself exists only as a pair (out_use 2
+// of an earlier layer) is read from that pair.
 Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k, int stride, int pad, int dil,
            bool relu, const Act* res, int out_use = 0) {
   int p = (kd == 1 && dil > 1) ? dil : pad;          // psm_submodule.convbn :13
@@ -381,9 +383,17 @@ Act convbn(Eng* e, const Act& x, const std::string& pre, int Cout, int kd, int k
       pb.lo = e->pool.acquire((size_t)y.floats() * 2);
       if (!pb.hi || !pb.lo) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return y; }
     }
+    const float* res_f = res ? res->p : nullptr;
+    const void *res_hi = nullptr, *res_lo = nullptr;
+    if (res && res->pair_only) {
+      auto it = e->pairs.find(res->p);
+      if (it == e->pairs.end()) { nrgbd_set_error("engine: residual has neither an fp32 copy nor an operand pair"); e->rc = NRGBD_ERR_BAD_ARG; return y; }
+      res_f = nullptr; res_hi = it->second.hi; res_lo = it->second.lo;
+    }
     ENG_CALL(e, nrgbd_bn_apply_stats_pair(y.p, e->stats, (double)y.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
-                                          0.1f, res ? res->p : nullptr, relu ? 1 : 0, y.pos(), y.Cs, y.C, (pair && out_use == 2) ? nullptr : y.p,
+                                          0.1f, res_f, res_hi, res_lo, relu ? 1 : 0, y.pos(), y.Cs, y.C, (pair && out_use == 2) ? nullptr : y.p,
                                           pb.hi, pb.lo, e->bn_counter, (nrgbd_stream_t)e->st));
+    y.pair_only = pair && out_use == 2;
     if (pair) e->pairs[y.p] = pb;
     return y;
   }
@@ -419,7 +429,8 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
     if (!e->rc) {
       if (e->conv_math == 2)
         ENG_CALL(e, nrgbd_bn_apply_stats_pair(sc.p, e->stats, (double)sc.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
-                                              0.1f, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, nullptr, nullptr, e->bn_counter, (nrgbd_stream_t)e->st));
+                                              0.1f, nullptr, nullptr, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, nullptr, nullptr, e->bn_counter,
+                                              (nrgbd_stream_t)e->st));
       else
       ENG_CALL(e, nrgbd_bn_apply_stats(sc.p, e->stats, (double)sc.pos(), g, b, 1e-5f, rm && rv ? rm : nullptr, rm && rv ? rv : nullptr,
                                        0.1f, nullptr, 0, sc.pos(), sc.Cs, sc.C, sc.p, (nrgbd_stream_t)e->st));
@@ -621,11 +632,12 @@ Act kv_net(Eng* e, const Act& vol) {
     return convbn(e, x, name, f, 3, 3, 1, 1, 1, relu, res, out_use);
   };
   Act a = cb(vol, "kv_net.dres0.0", true, nullptr, 2);
-  Act c = cb(a, "kv_net.dres0.2", true, nullptr, 1); release(e, a);      // also the residual of dres1
+  // in f16-pair mode no K-Net activation has an fp32 copy: convolutions read the operand pairs, and so do the residual adds
+  Act c = cb(a, "kv_net.dres0.2", true, nullptr, 2); release(e, a);      // also the residual of dres1
   for (int i = 1; i <= 4; ++i) {
     std::string p = "kv_net.dres" + std::to_string(i);
     Act r = cb(c, p + ".0", true, nullptr, 2);
-    Act o = cb(r, p + ".2", false, &c, i < 4 ? 1 : 2);                     // dres4's output feeds classify.0 only
+    Act o = cb(r, p + ".2", false, &c, 2);
     release(e, r); release(e, c);
     c = o;
   }
