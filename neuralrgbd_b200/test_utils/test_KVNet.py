@@ -35,7 +35,10 @@ def _stack_window(Ref_Dats, Src_Dats):
 def _next_prior(dpv_lowres, pose_to_next, cam_intrinsic, d_candi):
     """Step 4 for one batch entry: [D,h,w] log-DPV -> [1,D,h,w] prior in the next camera."""
     uniform_log = math.log(1.0 / float(len(d_candi)))
-    moved = warp_homo.resample_vol_cuda(src_vol=dpv_lowres.unsqueeze(0), rel_extM=pose_to_next.inverse(),
+    # Tensor.inverse() checks its LU status on the host, i.e. it waits for everything queued on the stream - the forward that
+    # was just launched; inv_ex returns the same inverse without the host round trip, so the step stays asynchronous
+    inv = torch.linalg.inv_ex(pose_to_next).inverse if pose_to_next.is_cuda else pose_to_next.inverse()
+    moved = warp_homo.resample_vol_cuda(src_vol=dpv_lowres.unsqueeze(0), rel_extM=inv,
                                         cam_intrinsic=cam_intrinsic, d_candi=d_candi, padding_value=uniform_log,
                                         clamp=(-1000., 0.))
     return moved.unsqueeze(0)
