@@ -408,7 +408,9 @@ bool takes_tc2(Eng* e, const Act& x, int Cout) {
 }
 
 // psm_submodule.BasicBlock :31-49
-Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, int dil, bool down) {
+// fp32_out: the block's output is read as an fp32 tensor by something other than a convolution / residual add (f16-pair mode:
+// otherwise only its operand pair is written)
+Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, int dil, bool down, bool fp32_out = true) {
   const int p1 = dil > 1 ? dil : 1;                  // psm_submodule.convbn :13
   // Fused form (tensor path): conv1 leaves its RAW output and per-channel sums; BN1 + ReLU are applied by conv2 while it
   // converts its operands (nrgbd_conv_nhwc_tc2_bn_in) - one read + one write of the 64/128-channel tensor less per block.
@@ -454,17 +456,19 @@ Act basic_block(Eng* e, Act& x, const std::string& pre, int planes, int stride, 
                                        0.1f, res->p, 0, o.pos(), o.Cs, o.C, o.p, (nrgbd_stream_t)e->st));
     }
   } else {
-    o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res, 1);
+    o = convbn(e, t, pre + ".conv2", planes, 1, 3, 1, 1, dil, false, res, fp32_out ? 1 : 2);
   }
   release(e, t);
   if (down) release(e, sc);
   return o;
 }
 
-Act make_layer(Eng* e, Act x, bool own_x, const std::string& pre, int planes, int blocks, int stride, int dil, bool down) {
+Act make_layer(Eng* e, Act x, bool own_x, const std::string& pre, int planes, int blocks, int stride, int dil, bool down,
+               bool fp32_out = true) {
   Act cur = x;
   for (int i = 0; i < blocks; ++i) {
-    Act o = basic_block(e, cur, pre + "." + std::to_string(i), planes, i == 0 ? stride : 1, dil, down && i == 0);
+    Act o = basic_block(e, cur, pre + "." + std::to_string(i), planes, i == 0 ? stride : 1, dil, down && i == 0,
+                        i == blocks - 1 ? fp32_out : false);
     if (i > 0 || own_x) release(e, cur);
     cur = o;
   }
@@ -505,11 +509,11 @@ void feature_cnn(Eng* e, const Act& x0, Act& l1_out, Act& feat_out) {
   } else {
     Act a = convbn(e, x0, P + ".firstconv.0", 32, 1, 3, 2, 1, 1, true, nullptr, 2);
     Act b = convbn(e, a, P + ".firstconv.2", 32, 1, 3, 1, 1, 1, true, nullptr, 2); release(e, a);
-    c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr, 1); release(e, b);
+    c = convbn(e, b, P + ".firstconv.4", 32, 1, 3, 1, 1, 1, true, nullptr, 2); release(e, b);     // layer1.0 reads it as conv input and as residual: pair only
   }
   Act l1 = make_layer(e, c, true, P + ".layer1", 32, 3, 1, 1, false);
   Act raw = make_layer(e, l1, false, P + ".layer2", 64, 16, 2, 1, true);
-  Act l3 = make_layer(e, raw, false, P + ".layer3", 128, 3, 1, 1, true);
+  Act l3 = make_layer(e, raw, false, P + ".layer3", 128, 3, 1, 1, true, false);     // feeds layer4 only (conv input + residual)
   Act skip = make_layer(e, l3, true, P + ".layer4", 128, 3, 1, 2, false);
   Act cat = acquire(e, skip.N, 1, skip.H, skip.W, 320);
   if (!e->rc) {
