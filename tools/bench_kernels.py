@@ -61,9 +61,6 @@ def main():
                                               ptr(ws), ptr(cost), st()))
     res = {}
     med, mn = timeit(sweep)
-            print(json.dumps(dict(shape=[h, w, C, V, D], sweep_variant=v, us_med=med, us_min=mn)), flush=True)
-        return
-    med, mn = timeit(sweep)
     alg = (1 + V) * C * hw * 4 + D * hw * 4 + 3 * hw * 4
     res['sweep'] = dict(us_med=med, us_min=mn, alg_MB=alg / 1e6, GBps=alg / med / 1e3,
                         gflops=V * D * hw * (11 * C + 30) / med / 1e3)
