@@ -66,7 +66,7 @@ CONFIGS = {
     'c4': dict(kind='stream', H=376, W=1248, D=128, V=4, r=2, intr=dict(fx=721.5377, fy=721.5377, cx=624.0, cy=188.0, d=(1.0, 60.0)), n_stream=12, inflight=2,
                workload='kitti1248x376_d128_v4_full_kvnet_stream (BASELINE.json configs[3]; 1242x375 is rejected by the reference CNN; SURVEY C4)',
                metric='depth frames/sec at 1248x376x128-plane x4-view, full KVNet, streaming'),
-    'c5': dict(kind='first', H=1080, W=1920, D=256, V=8, r=4, intr=dict(fx=1755.0, fy=1755.0, cx=960.0, cy=540.0, d=(0.1, 5.0)), inflight=1,
+    'c5': dict(kind='first', H=1080, W=1920, D=256, V=8, r=4, intr=dict(fx=1755.0, fy=1755.0, cx=960.0, cy=540.0, d=(0.1, 5.0)), inflight=2,
                workload='synthetic1920x1080_d256_v8_dnet_dpv_plus_rnet (BASELINE.json configs[4]; SURVEY C5)',
                metric='depth frames/sec at 1920x1080x256-plane x8-view'),
 }
