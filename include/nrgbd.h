@@ -290,6 +290,14 @@ int nrgbd_pack_conv_weight_h2(const float* w, int transposed, int Cout, int Cin,
 int nrgbd_conv_nhwc_h2(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const void* w,
                        const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride, int pad, int dilation,
                        float* y, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, nrgbd_stream_t stream);
+/* nrgbd_conv_nhwc_h2 with the result (after bias / LeakyReLU) written ONLY as the split-fp16 operand pair of the convolution
+ * that consumes it: y_hi / y_lo are half tensors [N][D][Hout][Wout][Cs_out], Cs_out % 32 == 0, every channel stored (pad
+ * channels as zeros). For conv -> conv chains without a BatchNorm in between (R-Net, models/Refine.py:79-107): saves the
+ * separate split pass. No statistics, no channel offset. */
+int nrgbd_conv_nhwc_h2_pair(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in,
+                            const void* w, const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride,
+                            int pad, int dilation, void* y_hi, void* y_lo, int Hout, int Wout, int Cs_out, int leaky,
+                            nrgbd_stream_t stream);
 int nrgbd_conv_transpose2d_k4s2_nhwc_h2(const void* x_hi, const void* x_lo, int N, int Hin, int Win, int Cin_pad, int Cs_in,
                                         const void* w, const float* bias, int Cout, int Cout_pad, int BN, float* y, int Cs_out,
                                         int c_off, int leaky, nrgbd_stream_t stream);

@@ -310,6 +310,32 @@ def conv_h2(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False, want_stat
     return (out, stats) if want_stats else out
 
 
+def conv_h2_pair_out(x, w, bias=None, stride=1, pad=0, dilation=1, leaky=False):
+    """conv_h2 whose result is written only as the operand pair of the next convolution (nrgbd_conv_nhwc_h2_pair). Returns the
+    fp32 value of the pair, hi + lo * 2^-11, as NCHW / NCDHW, and the raw (hi, lo) half tensors (channels-last, Cs = pad32)."""
+    L = _lib.lib()
+    is3d = x.dim() == 5
+    N = x.shape[0]
+    Din = x.shape[2] if is3d else 1
+    Hin, Win = x.shape[-2], x.shape[-1]
+    Cout, Cin = w.shape[0], w.shape[1]
+    wp, Cin_pad, Cout_pad, BN = pack_weight_h2(w)
+    xh, xl = split_f16_pair(to_cl_padded(x, Cin_pad))
+    kd = w.shape[2] if is3d else 1
+    kh, kw = w.shape[-2], w.shape[-1]
+    Ho = (Hin + 2 * pad - dilation * (kh - 1) - 1) // stride + 1
+    Wo = (Win + 2 * pad - dilation * (kw - 1) - 1) // stride + 1
+    Cs = pad_to(Cout, 32)
+    shape = (N,) + ((Din,) if is3d else ()) + (Ho, Wo, Cs)
+    # poisoned: every element, pad channels included, must be written by the kernel
+    yh = torch.full(shape, float('nan'), device=x.device, dtype=torch.float16)
+    yl = torch.full(shape, float('nan'), device=x.device, dtype=torch.float16)
+    check(L.nrgbd_conv_nhwc_h2_pair(ptr(xh), ptr(xl), N, Din, Hin, Win, Cin_pad, Cin_pad, ptr(wp), ptr(bias), Cout, Cout_pad, BN,
+                                    kd, kh, kw, stride, pad, dilation, ptr(yh), ptr(yl), Ho, Wo, Cs, 1 if leaky else 0, _st()))
+    val = yh.float() + yl.float() * (1.0 / 2048.0)
+    return from_cl(val.contiguous(), Cout), yh, yl
+
+
 def conv_cout1_h2(x, w, bias=0.0):
     """Single-output-channel k3 convolution (K-Net's last layer, models/basic.py:136-137) the way the engine runs it:
     a pointwise f16-pair conv to one channel per tap + nrgbd_tap_gather_sum. x [N, C, D, H, W] (or [N, C, H, W]),

@@ -43,6 +43,8 @@ constexpr float H_MAX = 65504.f;
 
 struct H2Params {
   float* y; const float* bias; double* stats;
+  void *y_hi, *y_lo;                     // pair_out: the output is written as the split-fp16 operand pair of the next convolution
+  int pair_out;
   int N, Dz, Hy, Wx, tiles_x, tiles_y;
   int cin_chunks, bkc, row_bytes;        // channels per K chunk (32 | 64), bytes of one pixel row of a tile (64 | 128)
   int n_kz, n_tap;                       // depth taps, in-plane taps
@@ -174,7 +176,8 @@ template <int NKS, int MSUB, int G>
 __global__ void __launch_bounds__(H2_THREADS, 1)
 conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_last,
-               const __grid_constant__ CUtensorMap tm_y, const H2Params p) {
+               const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_yh,
+               const __grid_constant__ CUtensorMap tm_yl, const H2Params p) {
   // shared memory: [A ring: stages_a x (hi tile | lo tile)][B ring: stages_b x ([b_hi rows | b_lo rows])][staging][barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -203,7 +206,11 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_b_last) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_y) : "memory");
+    if (p.tma_store && !p.pair_out) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_y) : "memory");
+    if (p.pair_out) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_yh) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_yl) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -419,6 +426,16 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int c0 = sl * 32 + half * 16;
+          if (c0 >= BN && p.pair_out) {
+            // pair output: the store covers the whole 32-channel slab (pad channels of the operand pair must be zero)
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            uint8_t* rowh = ep + r * 64;
+            const int sw = (r >> 1) & 3;
+            *reinterpret_cast<uint4*>(rowh + (((half * 2) ^ sw) << 4)) = z;
+            *reinterpret_cast<uint4*>(rowh + (((half * 2 + 1) ^ sw) << 4)) = z;
+            *reinterpret_cast<uint4*>(rowh + 8192 + (((half * 2) ^ sw) << 4)) = z;
+            *reinterpret_cast<uint4*>(rowh + 8192 + (((half * 2 + 1) ^ sw) << 4)) = z;
+          }
           if (c0 < BN) {
             uint32_t vm[16], vc[16];
             asm volatile(
@@ -450,14 +467,30 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 16; ++j) if (c0 + j >= n_here) f[j] = 0.f;
             }
-            if (tma_out || want_stats) {
+            if (p.pair_out) {
+              // two 64-byte-row half tiles [hi 8 KB | lo 8 KB] in the group's slab, 64-byte swizzle (chunk ^= row / 2 mod 4)
+              uint32_t hw[8], lw[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                __half h0, l0, h1, l1;
+                nrgbd_split_pair(f[j], h0, l0); nrgbd_split_pair(f[j + 1], h1, l1);
+                hw[j >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lw[j >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              }
+              uint8_t* rowh = ep + r * 64;
+              const int sw = (r >> 1) & 3;
+              *reinterpret_cast<uint4*>(rowh + (((half * 2) ^ sw) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(rowh + (((half * 2 + 1) ^ sw) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+              *reinterpret_cast<uint4*>(rowh + 8192 + (((half * 2) ^ sw) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              *reinterpret_cast<uint4*>(rowh + 8192 + (((half * 2 + 1) ^ sw) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+            } else if (tma_out || want_stats) {
               uint8_t* rowp = ep + r * 128;
               const int j0 = half * 4;
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj)
                 *reinterpret_cast<float4*>(rowp + (((j0 + jj) ^ (r & 7)) << 4)) = make_float4(f[4 * jj], f[4 * jj + 1], f[4 * jj + 2], f[4 * jj + 3]);
             }
-            if (valid && !tma_out && !(p.dev_flags & 32)) {
+            if (valid && !tma_out && !p.pair_out && !(p.dev_flags & 32)) {
               if (vec_ok && c0 + 16 <= n_here) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -472,7 +505,15 @@ conv_h2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged slab -> visible to the TMA engine
           if (cg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
         }
-        if (storer && sl * 32 < n_here) {
+        if (storer && p.pair_out) {
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"((uint64_t)&tm_yh), "r"(ep_addr), "r"(p.c_off + cbase + sl * 32), "r"(ox0), "r"(oy0), "r"(z0), "r"(n0)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                       ::"l"((uint64_t)&tm_yl), "r"(ep_addr + 8192u), "r"(p.c_off + cbase + sl * 32), "r"(ox0), "r"(oy0), "r"(z0), "r"(n0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (storer && sl * 32 < n_here) {
           asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                        ::"l"((uint64_t)&tm_y), "r"(ep_addr), "r"(p.c_off + cbase + sl * 32), "r"(ox0), "r"(oy0), "r"(z0), "r"(n0)
                        : "memory");
@@ -723,13 +764,28 @@ int launch_h2(const __half* x_hi, const __half* x_lo, int N, int Din, int Hin, i
   const size_t smem = ring + p.staging_bytes + 512;
   ty = ta_hi;
   p.tma_store = 0;
-  if (p.out_stride == 1 && p.out_off_y == 0 && p.out_off_x == 0 && p.Cs_out % 4 == 0 && p.c_off % 4 == 0 && ((uintptr_t)p.y & 15) == 0 &&
-      !(g_h2_flags & 2048)) {
+  if (!p.pair_out && p.out_stride == 1 && p.out_off_y == 0 && p.out_off_x == 0 && p.Cs_out % 4 == 0 && p.c_off % 4 == 0 &&
+      ((uintptr_t)p.y & 15) == 0 && !(g_h2_flags & 2048)) {
     rc = encode_cl_map(&ty, p.y, 4, N, p.Dout, p.Hout, p.Wout, p.c_off + p.Cout, p.Cs_out, 32, TW, TH, 1, 128);
     if (rc != NRGBD_OK) return rc;
     p.tma_store = 1;
   }
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const H2Params);
+  CUtensorMap tyh = ta_hi, tyl = ta_hi;
+  if (p.pair_out) {
+    // the output as the operand pair of the next convolution: two half tensors with the fp32 tensor's layout, all Cs_out
+    // channels stored (pad channels as zeros), 64-byte swizzled staging
+    if (!(p.out_stride == 1 && p.out_off_y == 0 && p.out_off_x == 0 && p.Cs_out % 32 == 0 && p.c_off == 0 && p.stats == nullptr &&
+          (((uintptr_t)p.y_hi | (uintptr_t)p.y_lo) & 15) == 0 && p.y_hi && p.y_lo)) {
+      nrgbd_set_error("conv_h2: pair output needs a dense stride-1 output with Cs_out % 32 == 0, c_off == 0 and no statistics");
+      return NRGBD_ERR_UNSUPPORTED;
+    }
+    rc = encode_cl_map(&tyh, p.y_hi, 2, N, p.Dout, p.Hout, p.Wout, p.Cs_out, p.Cs_out, 32, TW, TH, 1, 64);
+    if (rc == NRGBD_OK) rc = encode_cl_map(&tyl, p.y_lo, 2, N, p.Dout, p.Hout, p.Wout, p.Cs_out, p.Cs_out, 32, TW, TH, 1, 64);
+    if (rc != NRGBD_OK) return rc;
+    p.tma_store = 1;
+  }
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const CUtensorMap, const H2Params);
   KernelFn fn = nullptr;
   int slot = 0;
   if (p.bkc != 32) { nrgbd_set_error("conv_h2: only 32-channel chunks are instantiated"); return NRGBD_ERR_UNSUPPORTED; }
@@ -748,7 +804,7 @@ int launch_h2(const __half* x_hi, const __half* x_lo, int N, int Din, int Hin, i
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; }
   const long long items = (long long)N * p.Dz * p.tiles_x * p.tiles_y * n_chunks;      // tiles_y counts msub-high tiles
   const unsigned grid = (unsigned)(items < n_sm ? items : n_sm);
-  fn<<<grid, H2_THREADS, smem, st>>>(ta_hi, ta_lo, tb, tb_last, ty, p);
+  fn<<<grid, H2_THREADS, smem, st>>>(ta_hi, ta_lo, tb, tb_last, ty, tyh, tyl, p);
   return NRGBD_OK;
 }
 
@@ -792,10 +848,34 @@ int nrgbd_pack_conv_weight_h2(const float* w, int transposed, int Cout, int Cin,
   return NRGBD_OK;
 }
 
+static int conv_nhwc_h2_impl(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const void* w,
+                             const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride, int pad, int dilation, float* y,
+                             void* y_hi, void* y_lo, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, cudaStream_t st);
+
 int nrgbd_conv_nhwc_h2(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const void* w,
                        const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride, int pad, int dilation, float* y,
                        int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, cudaStream_t st) {
-  NRGBD_REQUIRE(x_hi && x_lo && w && y, "null pointer");
+  NRGBD_REQUIRE(y, "null pointer");
+  return conv_nhwc_h2_impl(x_hi, x_lo, N, Din, Hin, Win, Cin_pad, Cs_in, w, bias, Cout, Cout_pad, BN, kd, kh, kw, stride, pad, dilation, y, nullptr,
+                           nullptr, Hout, Wout, Cs_out, c_off, leaky, stats, st);
+}
+
+// Same convolution, the result (after bias / LeakyReLU) written ONLY as the split-fp16 operand pair of the convolution that
+// consumes it: y_hi / y_lo are half tensors [N][D][Hout][Wout][Cs_out], Cs_out % 32 == 0, every channel stored (pad channels
+// as zeros). Saves the separate split pass (one fp32 read + one pair write per element) for conv -> conv chains without a
+// BatchNorm in between (R-Net, models/Refine.py:79-107).
+int nrgbd_conv_nhwc_h2_pair(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const void* w,
+                            const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride, int pad, int dilation,
+                            void* y_hi, void* y_lo, int Hout, int Wout, int Cs_out, int leaky, cudaStream_t st) {
+  NRGBD_REQUIRE(y_hi && y_lo, "null pointer");
+  return conv_nhwc_h2_impl(x_hi, x_lo, N, Din, Hin, Win, Cin_pad, Cs_in, w, bias, Cout, Cout_pad, BN, kd, kh, kw, stride, pad, dilation, nullptr, y_hi,
+                           y_lo, Hout, Wout, Cs_out, 0, leaky, nullptr, st);
+}
+
+static int conv_nhwc_h2_impl(const void* x_hi, const void* x_lo, int N, int Din, int Hin, int Win, int Cin_pad, int Cs_in, const void* w,
+                             const float* bias, int Cout, int Cout_pad, int BN, int kd, int kh, int kw, int stride, int pad, int dilation, float* y,
+                             void* y_hi, void* y_lo, int Hout, int Wout, int Cs_out, int c_off, int leaky, double* stats, cudaStream_t st) {
+  NRGBD_REQUIRE(x_hi && x_lo && w, "null pointer");
   NRGBD_REQUIRE(Cin_pad % 32 == 0 && Cin_pad >= 32 && Cin_pad <= Cs_in && Cs_in % 8 == 0 && Cout_pad % 16 == 0 && Cout <= Cout_pad && Cout > Cout_pad - 16 &&
                     BN == (Cout_pad < 128 ? Cout_pad : 128), "channel counts not supported by the f16-pair tensor-core path");
   NRGBD_REQUIRE(kd >= 1 && kd <= 3 && kh * kw <= MAX_TAP2D && stride >= 1 && stride <= 8, "unsupported filter");
@@ -803,6 +883,7 @@ int nrgbd_conv_nhwc_h2(const void* x_hi, const void* x_lo, int N, int Din, int H
                     Wout == (Win + 2 * pad - dilation * (kw - 1) - 1) / stride + 1, "output extent mismatch");
   H2Params p{};
   p.y = y; p.bias = bias; p.stats = stats;
+  p.y_hi = y_hi; p.y_lo = y_lo; p.pair_out = y_hi ? 1 : 0;
   p.N = N; p.Dz = Din; p.Hy = Hout; p.Wx = Wout;
   p.in_stride = stride; p.Cout = Cout; p.BN = BN;
   p.Dout = Din; p.Hout = Hout; p.Wout = Wout; p.Cs_out = Cs_out; p.c_off = c_off;

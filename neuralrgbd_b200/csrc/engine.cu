@@ -302,13 +302,35 @@ void split_act(Eng* e, const Act& x, Act& hi, Act& lo) {
 }
 
 // conv (2-D when x.D == 1 and kd == 1) into a fresh activation or into `dst` at channel c_off
+// pair_out (f16-pair mode, no BatchNorm after the conv): the result is written only as the operand pair of the convolution that
+// consumes it (y.p is a 16-byte key of the pair, y.pair_only) - no fp32 tensor, no split pass
 Act conv(Eng* e, const Act& x, const std::string& wname, int Cout, int kd, int k, int stride, int pad, int dil,
          const char* bias_name, bool leaky, bool want_stats, Act* dst = nullptr, int c_off = 0, int out_Cs = -1,
-         double* stats_buf = nullptr, const nrgbd_bn_input* in_bn = nullptr) {
+         double* stats_buf = nullptr, const nrgbd_bn_input* in_bn = nullptr, bool pair_out = false) {
   if (!stats_buf) stats_buf = e->stats;
   int Ho = (x.H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
   int Wo = (x.W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
   Act y;
+  if (pair_out && use_h2(e, x) && Cout >= 16 && !dst && !want_stats && c_off == 0 && out_Cs < 0 && stride == 1) {
+    y.N = x.N; y.D = x.D; y.H = Ho; y.W = Wo; y.C = Cout; y.Cs = pad32(Cout); y.pair_only = true;
+    float* b = bias_name ? param(e, bias_name) : nullptr;
+    const PackedH2* ph = packw_h2(e, wname, Cout, x.C, kd * k * k, false);
+    const PairBuf* pin = pair_of(e, x);
+    if (e->rc) return y;
+    PairBuf pb;
+    y.p = e->pool.acquire(16);                                    // key of the pair buffers
+    pb.hi = e->pool.acquire((size_t)y.floats() * 2);
+    pb.lo = e->pool.acquire((size_t)y.floats() * 2);
+    if (!y.p || !pb.hi || !pb.lo) { nrgbd_set_error("engine: out of device memory"); e->rc = NRGBD_ERR_NOMEM; return y; }
+    e->pairs[y.p] = pb;
+    const double flops = 2.0 * (double)x.N * x.D * Ho * Wo * Cout * x.C * kd * k * k;
+    char tag[56];
+    snprintf(tag, sizeof(tag), "conv%dd k%d s%d d%d %d->%d %dx%dx%dx%d", kd > 1 ? 3 : 2, k, stride, dil, x.C, Cout, x.N, x.D, Ho, Wo);
+    ProfScope ps(e, 0, flops, tag);
+    ENG_CALL(e, nrgbd_conv_nhwc_h2_pair(pin->hi, pin->lo, x.N, x.D, x.H, x.W, ph->Cin_pad, x.Cs, ph->w, b, Cout, ph->Cout_pad, ph->BN, kd, k, k,
+                                        stride, pad, dil, pb.hi, pb.lo, Ho, Wo, y.Cs, leaky ? 1 : 0, (nrgbd_stream_t)e->st));
+    return y;
+  }
   if (dst) y = *dst; else y = acquire(e, x.N, x.D, Ho, Wo, Cout, out_Cs);
   float* b = bias_name ? param(e, bias_name) : nullptr;
   if (e->rc) return y;
@@ -609,20 +631,20 @@ void r_net(Eng* e, const float* bv_hwd, const float* feat_ref, int feat_Cs, cons
     ENG_CALL(e, nrgbd_copy_channels(bv_hwd, hw, D, 0, D, 1, in0.p, in0.Cs, 0, st));           // torch.exp(BV)
     ENG_CALL(e, nrgbd_copy_channels(feat_ref, hw, feat_Cs, 0, F, 0, in0.p, in0.Cs, D, st));
   }
-  Act a = conv(e, in0, "r_net.conv0.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0.0.bias", true, false); release(e, in0);
-  Act b = conv(e, a, "r_net.conv0_1.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0_1.0.bias", true, false); release(e, a);
+  Act a = conv(e, in0, "r_net.conv0.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0.0.bias", true, false, nullptr, 0, -1, nullptr, nullptr, true); release(e, in0);
+  Act b = conv(e, a, "r_net.conv0_1.0.weight", D + F, 1, 3, 1, 1, 1, "r_net.conv0_1.0.bias", true, false, nullptr, 0, -1, nullptr, nullptr, true); release(e, a);
   Act t0 = acquire(e, 1, 1, 2 * h, 2 * w, D + F / 2);
   conv_transpose(e, b, "r_net.trans_conv0.0.weight", "r_net.trans_conv0.0.bias", D, t0);
   if (!e->rc) ENG_CALL(e, nrgbd_copy_channels(l1_ref, 4 * hw, l1_Cs, 0, F / 2, 0, t0.p, t0.Cs, D, st));
   release(e, b);
-  Act c = conv(e, t0, "r_net.conv1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1.0.bias", true, false); release(e, t0);
-  Act d = conv(e, c, "r_net.conv1_1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1_1.0.bias", true, false); release(e, c);
+  Act c = conv(e, t0, "r_net.conv1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1.0.bias", true, false, nullptr, 0, -1, nullptr, nullptr, true); release(e, t0);
+  Act d = conv(e, c, "r_net.conv1_1.0.weight", D + F / 2, 1, 3, 1, 1, 1, "r_net.conv1_1.0.bias", true, false, nullptr, 0, -1, nullptr, nullptr, true); release(e, c);
   Act t1 = acquire(e, 1, 1, H, W, D + 3);
   conv_transpose(e, d, "r_net.trans_conv1.0.weight", "r_net.trans_conv1.0.bias", D, t1);
   if (!e->rc) ENG_CALL(e, nrgbd_copy_channels(frame_ref.p, (long long)H * W, frame_ref.Cs, 0, 3, 0, t1.p, t1.Cs, D, st));
   release(e, d);
-  Act f = conv(e, t1, "r_net.conv2.0.weight", D + 3, 1, 3, 1, 1, 1, "r_net.conv2.0.bias", true, false); release(e, t1);
-  Act g = conv(e, f, "r_net.conv2_1.0.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_1.0.bias", true, false); release(e, f);
+  Act f = conv(e, t1, "r_net.conv2.0.weight", D + 3, 1, 3, 1, 1, 1, "r_net.conv2.0.bias", true, false, nullptr, 0, -1, nullptr, nullptr, true); release(e, t1);
+  Act g = conv(e, f, "r_net.conv2_1.0.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_1.0.bias", true, false, nullptr, 0, -1, nullptr, nullptr, true); release(e, f);
   conv(e, g, "r_net.conv2_2.weight", D, 1, 3, 1, 1, 1, "r_net.conv2_2.bias", false, false, &out, 0, D); release(e, g);
   // F.log_softmax(conv2_2_out, dim=1): channels are contiguous per pixel (Cs == D)
   if (!e->rc)

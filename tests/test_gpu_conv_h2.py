@@ -99,6 +99,27 @@ def test_conv3d_single_output_channel_tap_gather_vs_oracle():
     assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
 
 
+@pytest.mark.parametrize('cin,cout,hw', [(128, 128, (30, 40)), (96, 96, (37, 45)), (67, 67, (33, 24)), (64, 64, (16, 8)), (192, 160, (20, 19)),
+                                          (131, 131, (18, 25))])
+def test_conv2d_h2_pair_output_vs_oracle(cin, cout, hw):
+    """R-Net's conv -> conv chains (models/Refine.py:79-107: 3x3 conv + bias + LeakyReLU): the epilogue writes the operand pair
+    of the next convolution directly. The pair's value must match the oracle like the fp32 output does, the pad channels must
+    be written as zeros, and the halves must be exactly the split of a value (lo within the residual range)."""
+    from neuralrgbd_b200 import convops
+    rng = np.random.RandomState(cin + cout)
+    x = rng.standard_normal((1, cin) + hw).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, 3, 3)) / math.sqrt(cin * 9)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    y, yh, yl = convops.conv_h2_pair_out(T(x), T(w), T(b), 1, 1, 1, leaky=True)
+    ref = N.conv2d(x, w, b, 1, 1, 1)
+    ref = np.where(ref >= 0, ref, ref * np.float32(0.01))
+    assert y.shape == ref.shape and rel_err(y.cpu().numpy(), ref) <= 6e-6
+    yh_, yl_ = yh.float().cpu().numpy(), yl.float().cpu().numpy()
+    assert np.isfinite(yh_).all() and np.isfinite(yl_).all()                  # every element written, pad channels included
+    assert not yh_[..., cout:].any() and not yl_[..., cout:].any()
+    assert (np.abs(yl_) <= np.maximum(np.abs(yh_), 0.125) * 1.0001).all()        # |lo| <= ulp(hi)/2 * 2^11 <= |hi|
+
+
 def test_conv_transpose2d_h2_vs_oracle():
     from neuralrgbd_b200 import convops
     rng = np.random.RandomState(3)
