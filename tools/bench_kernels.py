@@ -123,6 +123,24 @@ def main():
     res['knet_input_volume_f32'] = dict(us_med=med, us_min=mn, GBps=(D * hw * 32 * 4 + 2 * D * hw * 4) / med / 1e3)
     med, mn = timeit(knet_pair)
     res['knet_input_volume_pair'] = dict(us_med=med, us_min=mn, GBps=(D * hw * 32 * 4 + 2 * D * hw * 4) / med / 1e3)
+    # BatchNorm pass over a K-Net volume [D][hw][64] (statistics -> scale / shift, ReLU, operand-pair output; with a pair residual)
+    xk = torch.randn(D * hw, 64, device=dev)
+    st64 = torch.stack([xk.double().sum(0), (xk.double() ** 2).sum(0)]).contiguous()
+    gam = torch.rand(64, device=dev) + 0.5; bet = torch.randn(64, device=dev)
+    yh = torch.empty(D * hw, 64, device=dev, dtype=torch.float16); yl = torch.empty_like(yh)
+    rh = torch.randn(D * hw, 64, device=dev).half(); rl = torch.zeros_like(rh)
+
+    def bn_plain():
+        check(L.nrgbd_bn_apply_stats_pair(ptr(xk), ctypes.c_void_p(st64.data_ptr()), float(D * hw), ptr(gam), ptr(bet), F(1e-5), None, None, F(0.1), None, None,
+                                          None, 1, D * hw, 64, 64, None, ptr(yh), ptr(yl), None, st()))
+
+    def bn_res():
+        check(L.nrgbd_bn_apply_stats_pair(ptr(xk), ctypes.c_void_p(st64.data_ptr()), float(D * hw), ptr(gam), ptr(bet), F(1e-5), None, None, F(0.1), None, ptr(rh),
+                                          ptr(rl), 0, D * hw, 64, 64, None, ptr(yh), ptr(yl), None, st()))
+    med, mn = timeit(bn_plain)
+    res['bn_pass_knet_volume_relu_pair'] = dict(us_med=med, us_min=mn, alg_MB=D * hw * 64 * 8 / 1e6, GBps=D * hw * 64 * 8 / med / 1e3)
+    med, mn = timeit(bn_res)
+    res['bn_pass_knet_volume_pair_residual'] = dict(us_med=med, us_min=mn, alg_MB=D * hw * 64 * 12 / 1e6, GBps=D * hw * 64 * 12 / med / 1e3)
     Hf, Wf = 4 * h, 4 * w
     imgs = torch.randn(V, 3, Hf, Wf, device=dev); dm_full = (0.8 + 2.5 * torch.rand(Hf, Wf, device=dev))
     xsf = (np.arange(Wf) + .5) / Wf * 2 - 1; ysf = (np.arange(Hf) + .5) / Hf * 2 - 1
