@@ -15,7 +15,8 @@ void nrgbd_conv_tc_set_dev(int stages, int flags); /* ring depth cap; A/B flags 
 void nrgbd_conv_tc_set_debug_buffer(long long* device_buf); /* [grid][64] clock64 stamps (tools/tc_timeline.py) */
 int nrgbd_mma_probe(int BN, int n_mma, int pattern, int nd, int grp, int two_warps, int n_ctas, long long* out,
                     nrgbd_stream_t stream);        /* raw tcgen05.mma issue / execution rate probe */
-void nrgbd_dev_set_bn_unroll(int u);               /* BatchNorm pass: 16-byte vectors in flight per thread (1, 2 or 4) */
+void nrgbd_dev_set_bn_blocks_per_sm(int b);      /* BatchNorm pass: grid cap in blocks per SM (0 = chosen by tensor size: 8, or 32 from 128 MB) */
+void nrgbd_dev_set_bn_unroll(int u);               /* BatchNorm pass: 16-byte vectors in flight per thread (1, 2 or 4; 0 = chosen by tensor size) */
 void nrgbd_dev_conv_h2_set_flags(int flags);       /* conv_f16.cu variants: flags listed next to g_h2_flags */
 void nrgbd_dev_conv_h2_set_smem_cap_kb(int kb);    /* cap on conv_h2's dynamic shared memory (0 = maximum): co-residency experiments */
 void nrgbd_dev_conv_h2_set_debug_buffer(long long* device_buf); /* [grid.y][grid.x][16] clock64 stamps (tools/h2_timeline.py) */

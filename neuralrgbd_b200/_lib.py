@@ -114,6 +114,7 @@ DEV_SIGNATURES = {
     'nrgbd_conv_tc_set_debug_buffer': (None, [c_vp]),
     'nrgbd_mma_probe': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'nrgbd_dev_set_bn_unroll': (None, [c_int]),
+    'nrgbd_dev_set_bn_blocks_per_sm': (None, [c_int]),
     'nrgbd_dev_conv_h2_set_flags': (None, [c_int]),
     'nrgbd_dev_conv_h2_set_debug_buffer': (None, [c_vp]),
     'nrgbd_dev_conv_h2_set_smem_cap_kb': (None, [c_int]),

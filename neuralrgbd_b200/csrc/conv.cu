@@ -410,13 +410,18 @@ tap_gather_sum_kernel(const float* __restrict__ Q, int D, int H, int W, int Cs, 
   out[((size_t)nd * H + y) * W + x] = acc;
 }
 
-int g_bn_unroll = 1;      // vectors in flight per thread in the BatchNorm pass (development knob, nrgbd_dev_set_bn_unroll)
+// BatchNorm pass shape, measured over a K-Net volume (1248x376 / 4, D = 128, 64 channels; tools/bench_kernels.py bnsweep): one vector
+// per thread and 8 blocks per SM 418 us (4.6 TB/s) / 680 us with a pair residual; TWO vectors in flight and 32 blocks per SM
+// 333 us (5.8 TB/s) / 471 us (6.1 TB/s = 93 % of the measured copy bandwidth); four vectors 343 / 535 us.
+int g_bn_unroll = 0;           // development override of the vectors in flight per thread (0 = by size; nrgbd_dev_set_bn_unroll)
+int g_bn_blocks_per_sm = 0;    // development override of the grid cap in blocks per SM (0 = by size; nrgbd_dev_set_bn_blocks_per_sm)
 
 }  // namespace
 
 extern "C" {
 
 void nrgbd_dev_set_bn_unroll(int u) { g_bn_unroll = u; }
+void nrgbd_dev_set_bn_blocks_per_sm(int b) { g_bn_blocks_per_sm = b; }
 
 int nrgbd_pack_conv_weight(const float* w, int transposed, int Cout, int Cin, int taps, int Cin_pad, int Cout_pad,
                            float* out, cudaStream_t st) {
@@ -561,12 +566,17 @@ int nrgbd_bn_apply_stats_pair(const float* x, double* stats, double count, const
   const uint2* rl = reinterpret_cast<const uint2*>(res_lo);
   long long n4 = n_pos * Cs / 4;
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (g_bn_unroll == 4)
+  // streaming shape (two vectors in flight, 32 blocks per SM) for tensors that do not fit L2 anyway (>= 128 MB of fp32: K-Net volumes,
+  // the 1080p feature maps); the small 2-D passes of a 640x480 frame are launch / L2-latency bound and keep the light shape
+  const bool big = n4 >= (8ll << 20);
+  const int unroll = g_bn_unroll > 0 ? g_bn_unroll : (big ? 2 : 1);
+  const long long cap = 148ll * (g_bn_blocks_per_sm > 0 ? g_bn_blocks_per_sm : (big ? 32 : 8));
+  if (blocks > cap) blocks = cap;
+  if (unroll == 4)
     bn_apply_stats_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, rh, rl,
                                                               relu, n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
                                                               rezero_counter ? stats : nullptr, rezero_counter);
-  else if (g_bn_unroll == 2)
+  else if (unroll == 2)
     bn_apply_stats_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, stats, count, gamma, beta, eps, run_mean, run_var, momentum, res, rh, rl,
                                                               relu, n4, Cs, C, y, reinterpret_cast<uint2*>(y_hi), reinterpret_cast<uint2*>(y_lo),
                                                               rezero_counter ? stats : nullptr, rezero_counter);

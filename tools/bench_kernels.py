@@ -35,7 +35,7 @@ def timeit(fn, iters=20, warm=3):
 
 def main():
     h, w, C, V, D = 120, 160, 67, 4, 64
-    pos = [a for a in sys.argv[1:] if '=' not in a]
+    pos = [a for a in sys.argv[1:] if '=' not in a and a != 'bnsweep']
     if pos:
         h, w, C, V, D = [int(x) for x in pos[:5]]
     hw = h * w
@@ -137,6 +137,14 @@ def main():
     def bn_res():
         check(L.nrgbd_bn_apply_stats_pair(ptr(xk), ctypes.c_void_p(st64.data_ptr()), float(D * hw), ptr(gam), ptr(bet), F(1e-5), None, None, F(0.1), None, ptr(rh),
                                           ptr(rl), 0, D * hw, 64, 64, None, ptr(yh), ptr(yl), None, st()))
+    if 'bnsweep' in sys.argv:          # development: vectors in flight per thread x grid cap
+        DL = _lib.dev_lib()
+        for u in (1, 2, 4):
+            for bps in (4, 8, 16, 32):
+                DL.nrgbd_dev_set_bn_unroll(u); DL.nrgbd_dev_set_bn_blocks_per_sm(bps)
+                a, _ = timeit(bn_plain); b, _ = timeit(bn_res)
+                print(json.dumps(dict(unroll=u, blocks_per_sm=bps, plain_us=a, plain_GBps=D * hw * 64 * 8 / a / 1e3, res_us=b, res_GBps=D * hw * 64 * 12 / b / 1e3)), flush=True)
+        return
     med, mn = timeit(bn_plain)
     res['bn_pass_knet_volume_relu_pair'] = dict(us_med=med, us_min=mn, alg_MB=D * hw * 64 * 8 / 1e6, GBps=D * hw * 64 * 8 / med / 1e3)
     med, mn = timeit(bn_res)
